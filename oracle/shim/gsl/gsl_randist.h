@@ -1,0 +1,1 @@
+/* Empty shim: see gsl_rng.h in this directory. */

@@ -1,0 +1,287 @@
+"""Python host layer over the C-ABI of ``libfscl_b200.so`` (include/fscl_b200.h).
+
+Mirrors the reference's scan entry points (slowkoni/fscl ``fscl.h:103-116``):
+
+* ``Scanner.scan_chromosome(G)``      <- ``scan_chromosome``  scan-chromosome.c:228
+* ``Scanner.scan_permute(pts, ...)``  <- ``scan_permute``     scan-chromosome.c:582
+* ``Scanner.grid_eval(chr, pos)``     <- ``init_scan_result`` + ``search_maxalpha``
+* ``format_records(...)``             <- ``scan_output``      scan-chromosome.c:666
+
+There is no CPU path: construction fails when the CUDA library is missing or no
+sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfscl_b200.so")
+NULL_SAVE = 10000
+
+RNG_GLIBC, RNG_PHILOX, RNG_LIBC = 0, 1, 2
+DEFAULT_SEED = 0xFD821A6          # srand() at fscl.c:135
+
+
+class FsclError(RuntimeError):
+    pass
+
+
+class fscl_problem_t(C.Structure):
+    _fields_ = [("n_snps", C.c_int32), ("chr", C.c_void_p), ("pos", C.c_void_p), ("cls", C.c_void_p),
+                ("n_chr", C.c_int32), ("chr_start", C.c_void_p), ("chr_nsnps", C.c_void_p),
+                ("chr_startpos", C.c_void_p), ("chr_bplen", C.c_void_p), ("n_cls", C.c_int32),
+                ("n_knots", C.c_int32), ("step", C.c_double), ("coef", C.c_void_p), ("null_tab", C.c_void_p),
+                ("log_table", C.c_void_p), ("eval_range", C.c_int32), ("bp_resl", C.c_int32),
+                ("device", C.c_int32), ("max_round_perms", C.c_int32)]
+
+
+class fscl_permute_opts_t(C.Structure):
+    _fields_ = [("n_permute", C.c_int32), ("permute_nbp", C.c_double), ("large_grid_sp", C.c_int32),
+                ("scan_width_mb", C.c_double), ("rng_kind", C.c_int32), ("seed", C.c_uint64),
+                ("prune", C.c_int32), ("first_perm", C.c_int32), ("perm_stride", C.c_int32),
+                ("round_perms", C.c_int32)]
+
+
+class fscl_stats_t(C.Structure):
+    _fields_ = [("n_scored", C.c_int64), ("n_tasks", C.c_int64), ("n_grid_evals", C.c_int64),
+                ("n_rounds", C.c_int64), ("n_blocks", C.c_int64), ("d7_hits", C.c_int32),
+                ("reserved", C.c_int32), ("score_kernel_ms", C.c_double), ("permute_kernel_ms", C.c_double),
+                ("score_launches", C.c_int64), ("permute_launches", C.c_int64)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+PT_DTYPE = np.dtype([("chr", "<i4"), ("nearest_snp", "<i4"), ("sweep_pos", "<i4"), ("n_snps", "<i4"),
+                     ("window_start", "<i4"), ("window_end", "<i4"), ("lalpha", "<f8"), ("null_logl", "<f8"),
+                     ("sm_logl", "<f8"), ("clr", "<f8"), ("permute_n", "<i4"), ("permute_p", "<i4"),
+                     ("permute_finished", "<i4"), ("reserved", "<i4")])
+assert PT_DTYPE.itemsize == 72
+
+EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy", "fscl_enum_cells",
+           "fscl_grid_eval", "fscl_search_maxpos", "fscl_scan_chromosome", "fscl_block_permute",
+           "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
+           "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak"]
+
+_lib = None
+
+
+def load_library(path=LIB_PATH):
+    """dlopen the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise FsclError(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(fscl_b200 has no CPU fallback)")
+    L = C.CDLL(path)
+    vp, ci = C.c_void_p, C.c_int
+    L.fscl_last_error.restype = C.c_char_p
+    L.fscl_create.argtypes = [vp, vp]
+    L.fscl_destroy.argtypes = [vp]
+    L.fscl_destroy.restype = None
+    L.fscl_enum_cells.argtypes = [vp, ci, vp, vp, vp, ci]
+    L.fscl_grid_eval.argtypes = [vp, ci, vp, vp, vp]
+    L.fscl_search_maxpos.argtypes = [vp, ci, vp, vp, vp, vp]
+    L.fscl_scan_chromosome.argtypes = [vp, ci, vp, ci, vp]
+    L.fscl_block_permute.argtypes = [vp, vp, ci, vp, vp, ci]
+    L.fscl_scan_permute.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.fscl_perm_begin.argtypes = [vp, vp, ci, vp, vp]
+    L.fscl_perm_round_score.argtypes = [vp, vp, C.c_int64, vp, vp]
+    L.fscl_perm_round_commit.argtypes = [vp, vp]
+    L.fscl_perm_end.argtypes = [vp, vp]
+    L.fscl_bench_scan.argtypes = [vp, ci, ci, ci, vp, vp]
+    L.fscl_get_stats.argtypes = [vp, vp]
+    L.fscl_reset_stats.argtypes = [vp]
+    L.fscl_fp64_peak.argtypes = [ci, vp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise FsclError(f"fscl_b200 error {rc}: {_lib.fscl_last_error().decode()}")
+
+
+def fp64_peak_tflops(device=0):
+    L = load_library()
+    v = C.c_double(0)
+    _check(L.fscl_fp64_peak(device, C.byref(v)))
+    return v.value
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Scanner:
+    """One problem resident on one GPU.  ``flat`` holds the flattened arrays the
+    C-ABI takes (see include/fscl_b200.h ``fscl_problem_t``)."""
+
+    def __init__(self, flat, device=0, eval_range=81920, bp_resl=128, log_table=None):
+        self.L = load_library()
+        self._ctx = C.c_void_p(None)
+        k = self._keep = {n: _i32(flat[n]) for n in
+                          ("chr", "pos", "cls", "chr_start", "chr_nsnps", "chr_startpos", "chr_bplen")}
+        k["coef"] = np.ascontiguousarray(flat["coef"], dtype=np.float64)
+        k["null_tab"] = np.ascontiguousarray(flat["null_tab"], dtype=np.float64)
+        if log_table is not None:
+            k["log_table"] = np.ascontiguousarray(log_table, dtype=np.float64)
+            assert k["log_table"].shape == (65536,)
+        self.chr_names = list(flat.get("chr_names", [str(i) for i in range(len(k["chr_start"]))]))
+        self.n_snps = len(k["pos"])
+        p = fscl_problem_t(self.n_snps, k["chr"].ctypes.data, k["pos"].ctypes.data, k["cls"].ctypes.data,
+                           len(k["chr_start"]), k["chr_start"].ctypes.data, k["chr_nsnps"].ctypes.data,
+                           k["chr_startpos"].ctypes.data, k["chr_bplen"].ctypes.data, len(k["null_tab"]),
+                           int(flat["n_knots"]), float(flat["step"]), k["coef"].ctypes.data,
+                           k["null_tab"].ctypes.data,
+                           k["log_table"].ctypes.data if log_table is not None else None,
+                           eval_range, bp_resl, device, 0)
+        _check(self.L.fscl_create(C.byref(p), C.byref(self._ctx)))
+        self.device = device
+
+    def close(self):
+        if self._ctx:
+            self.L.fscl_destroy(self._ctx)
+            self._ctx = C.c_void_p(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- forward scan ---------------------------------------------------
+    def enum_cells(self, G):
+        n = self.L.fscl_enum_cells(self._ctx, G, None, None, None, 0)
+        if n < 0:
+            _check(2)
+        cc = np.zeros((3, max(n, 1)), dtype=np.int32)
+        self.L.fscl_enum_cells(self._ctx, G, cc[0].ctypes.data, cc[1].ctypes.data, cc[2].ctypes.data, n)
+        return cc[:, :n]
+
+    def grid_eval(self, chr_, pos):
+        chr_, pos = _i32(np.atleast_1d(chr_)), _i32(np.atleast_1d(pos))
+        out = np.zeros(len(pos), dtype=PT_DTYPE)
+        _check(self.L.fscl_grid_eval(self._ctx, len(pos), chr_.ctypes.data, pos.ctypes.data, out.ctypes.data))
+        return out
+
+    def search_maxpos(self, chr_, start, end):
+        chr_, start, end = _i32(np.atleast_1d(chr_)), _i32(np.atleast_1d(start)), _i32(np.atleast_1d(end))
+        out = np.zeros(len(start), dtype=PT_DTYPE)
+        _check(self.L.fscl_search_maxpos(self._ctx, len(start), chr_.ctypes.data, start.ctypes.data,
+                                         end.ctypes.data, out.ctypes.data))
+        return out
+
+    def scan_chromosome(self, G):
+        n = self.L.fscl_enum_cells(self._ctx, G, None, None, None, 0)
+        out = np.zeros(max(n, 1), dtype=PT_DTYPE)
+        n_out = C.c_int(0)
+        _check(self.L.fscl_scan_chromosome(self._ctx, G, out.ctypes.data, len(out), C.byref(n_out)))
+        return out[:n_out.value]
+
+    # ---- permutations -----------------------------------------------------
+    @staticmethod
+    def permute_opts(n_permute, G, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DEFAULT_SEED, prune=1,
+                     first_perm=0, perm_stride=1, round_perms=0):
+        return fscl_permute_opts_t(n_permute, nbp, G, width_mb, rng, seed, prune, first_perm, perm_stride,
+                                   round_perms)
+
+    def block_permute(self, t, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DEFAULT_SEED, max_blocks=1 << 16):
+        o = self.permute_opts(0, 1, nbp, width_mb, rng, seed)
+        cls = np.zeros(self.n_snps, dtype=np.int32)
+        blocks = np.zeros((max_blocks, 3), dtype=np.int32)
+        nb = self.L.fscl_block_permute(self._ctx, C.byref(o), t, cls.ctypes.data, blocks.ctypes.data, max_blocks)
+        if nb < 0:
+            _check(1)
+        return cls, blocks[:min(nb, max_blocks)]
+
+    def scan_permute(self, pts, n_permute, G, save_clr=False, **kw):
+        pts = np.ascontiguousarray(pts.copy())
+        o = self.permute_opts(n_permute, G, **kw)
+        clr = np.zeros((len(pts), NULL_SAVE), dtype=np.float32) if save_clr else None
+        st = fscl_stats_t()
+        _check(self.L.fscl_scan_permute(self._ctx, pts.ctypes.data, len(pts), C.byref(o),
+                                        clr.ctypes.data if save_clr else None, C.byref(st)))
+        return pts, st.asdict(), clr
+
+    def scan_permute_sharded(self, pts, n_permute, G, rank, world, allreduce, matrix, matrix_ptr, save_clr=False,
+                             **kw):
+        """Permutations sharded over ``world`` ranks (one process per GPU).
+
+        ``matrix`` is a device buffer of float64 owned by the caller (for example
+        a torch tensor), ``matrix_ptr`` its device address, and
+        ``allreduce(matrix, n_elems)`` sums its first n_elems over the ranks
+        (NCCL over NVLink).  Every rank ends with identical counts."""
+        pts = np.ascontiguousarray(pts.copy())
+        o = self.permute_opts(n_permute, G, first_perm=rank, perm_stride=world, **kw)
+        clr = np.zeros((len(pts), NULL_SAVE), dtype=np.float32) if save_clr else None
+        _check(self.L.fscl_perm_begin(self._ctx, pts.ctypes.data, len(pts), C.byref(o),
+                                      clr.ctypes.data if save_clr else None))
+        R, na = C.c_int(0), C.c_int(0)
+        cap = matrix.numel() if hasattr(matrix, "numel") else len(matrix)
+        while True:
+            _check(self.L.fscl_perm_round_score(self._ctx, matrix_ptr, cap, C.byref(R), C.byref(na)))
+            if R.value == 0:
+                break
+            allreduce(matrix, R.value * na.value)
+            _check(self.L.fscl_perm_round_commit(self._ctx, matrix_ptr))
+        st = fscl_stats_t()
+        _check(self.L.fscl_perm_end(self._ctx, C.byref(st)))
+        return pts, st.asdict(), clr
+
+    # ---- measurement --------------------------------------------------------
+    def bench_scan(self, G, n_perm_slots, count_terms=False):
+        terms = C.c_int64(0)
+        st = fscl_stats_t()
+        _check(self.L.fscl_bench_scan(self._ctx, G, n_perm_slots, int(count_terms), C.byref(terms), C.byref(st)))
+        return terms.value, st.asdict()
+
+    def stats(self):
+        st = fscl_stats_t()
+        _check(self.L.fscl_get_stats(self._ctx, C.byref(st)))
+        return st.asdict()
+
+    def reset_stats(self):
+        _check(self.L.fscl_reset_stats(self._ctx))
+
+    # ---- output -------------------------------------------------------------
+    def format_records(self, pts, n_permute=0, label=None, maximum_only=False):
+        return format_records(pts, self.chr_names, self._keep["pos"], n_permute, label, maximum_only)
+
+
+def _c_fmt_e(v):
+    """printf("%1.3e")"""
+    if v == 0 or not math.isfinite(v):
+        return "%1.3e" % v
+    return "%1.3e" % v
+
+
+def format_records(pts, chr_names, pos, n_permute=0, label=None, maximum_only=False):
+    """scan_output records (scan-chromosome.c:707-746)."""
+    pre = f"{label}\t" if label else ""
+    out = []
+    if maximum_only:
+        best = 0
+        for i in range(1, len(pts)):
+            if pts[i]["clr"] > pts[best]["clr"]:
+                best = i
+        p = pts[best]
+        return (f"{pre}{chr_names[p['chr']]}\t{p['sweep_pos']}\t{'%1.2f' % p['clr']}\t"
+                f"{_c_fmt_e(math.exp(p['lalpha']))}\t{p['n_snps']}\t{pos[p['window_start']]}\t"
+                f"{pos[p['window_end']]}\n")
+    for p in pts:
+        head = f"{pre}{chr_names[p['chr']]}\t{p['sweep_pos']}\t{'%1.2f' % p['clr']}\t{_c_fmt_e(math.exp(p['lalpha']))}"
+        if n_permute > 0:
+            if p["permute_p"] < 2:
+                pv = 1.0 / p["permute_n"]
+            else:
+                pv = (p["permute_p"] - 1.0) / (p["permute_n"] - 1.0)
+            out.append(f"{head}\t{p['permute_p']}\t{p['permute_n']}\t{'%1.3f' % (-math.log10(pv))}\n")
+        else:
+            out.append(f"{head}\t{p['n_snps']}\t{pos[p['window_start']]}\t{pos[p['window_end']]}\n")
+    return "".join(out)

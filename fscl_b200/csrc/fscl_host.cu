@@ -1,0 +1,785 @@
+// fscl_host.cu -- host side of libfscl_b200.so: context, block-permutation
+// generator, permutation rounds, the C-ABI of include/fscl_b200.h.
+//
+// Reference map (slowkoni/fscl):
+//   fscl_scan_chromosome  <- scan_chromosome      scan-chromosome.c:228-266
+//   fscl_scan_permute     <- scan_permute(_thread) scan-chromosome.c:412-652
+//   BlockGen::generate    <- snp_block_permute    scan-chromosome.c:345-363 (draw phase)
+//   GlibcRand             <- glibc 2.39 random_r TYPE_3 (srand fscl.c:135)
+#include "../../include/fscl_b200.h"
+#include "fscl_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace fscl;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &m) { g_err = m; return code; }
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(FSCL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));              \
+  } while (0)
+
+extern "C" const char *fscl_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fscl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// --------------------------------------------------------------------------- RNG
+namespace {
+
+struct GlibcRand {            // r[i] = r[i-31] + r[i-3]; output >> 1; 310 warm-up draws
+  int32_t r[34];
+  long k;
+  void seed(unsigned s) {
+    int32_t w[344];
+    if (s == 0) s = 1;
+    w[0] = (int32_t)s;
+    for (int i = 1; i < 31; i++) {
+      long hi = w[i - 1] / 127773, lo = w[i - 1] % 127773;
+      long v = 16807 * lo - 2836 * hi;
+      if (v < 0) v += 2147483647;
+      w[i] = (int32_t)v;
+    }
+    for (int i = 31; i < 34; i++) w[i] = w[i - 31];
+    for (int i = 34; i < 344; i++) w[i] = (int32_t)((uint32_t)w[i - 31] + (uint32_t)w[i - 3]);
+    for (int i = 310; i < 344; i++) r[i % 34] = w[i];
+    k = 344;
+  }
+  int32_t next() {
+    uint32_t v = (uint32_t)r[(k - 31) % 34] + (uint32_t)r[(k - 3) % 34];
+    r[k % 34] = (int32_t)v;
+    k++;
+    if (k >= 34L * 1000000) k -= 34L * 999999;
+    return (int32_t)(v >> 1);
+  }
+};
+
+inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 31-bit draw, same range as rand(): counter = (idx, stream, t, 0), key = seed
+inline int32_t philox_draw(uint64_t seed, uint32_t t, uint32_t stream, uint32_t idx) {
+  uint32_t o[4];
+  philox4x32_10(idx, stream, t, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+  return (int32_t)(o[0] >> 1);
+}
+
+struct DrawSource {
+  int kind = FSCL_RNG_PHILOX;
+  uint64_t seed = 0;
+  GlibcRand g;
+  uint32_t t = 0, ctr = 0;
+  void init(int kind_, uint64_t seed_) {
+    kind = kind_; seed = seed_;
+    if (kind == FSCL_RNG_GLIBC) g.seed((unsigned)seed);
+  }
+  void set_perm(uint32_t t_) { t = t_; ctr = 0; }
+  int32_t block_draw() {
+    if (kind == FSCL_RNG_GLIBC) return g.next();
+    if (kind == FSCL_RNG_LIBC) return (int32_t)rand();
+    return philox_draw(seed, t, 0, ctr++);
+  }
+  int32_t prune_draw(uint32_t perm, uint32_t scan_pt) {
+    if (kind == FSCL_RNG_GLIBC) return g.next();
+    if (kind == FSCL_RNG_LIBC) return (int32_t)rand();
+    return philox_draw(seed, perm, 1, scan_pt);
+  }
+  bool sequential() const { return kind != FSCL_RNG_PHILOX; }
+};
+
+struct PermState {
+  bool open = false;
+  fscl_permute_opts_t o{};
+  int stride = 1;
+  DrawSource src;
+  fscl_pt_t *pts = nullptr;
+  int n_pts = 0;
+  float *permute_clr = nullptr;
+  std::vector<int> active, my_rows, off;
+  std::vector<int4> blocks;
+  std::vector<double> h_matrix;
+  double *d_matrix = nullptr;
+  int t_next = 0, R = 0;
+};
+
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Params P{};
+  int n = 0, n_chr = 0, n_cls = 0;
+  std::vector<int> h_chr, h_pos, h_cls, chr_start, chr_nsnps, chr_startpos, chr_bplen;
+  std::vector<int> chr_end_index;         // per SNP: one past the last index of its chromosome
+  // device
+  int *d_pos = nullptr, *d_cls0 = nullptr, *d_chr_start = nullptr, *d_chr_nsnps = nullptr;
+  double *d_coefK = nullptr, *d_logT = nullptr, *d_null = nullptr;
+  int max_slots = 0;
+  int *d_pcls = nullptr, *d_scratch = nullptr;
+  int4 *d_blocks = nullptr; size_t blocks_cap = 0;
+  int *d_blkoff = nullptr;
+  Task *d_tasks = nullptr; OutPt *d_out = nullptr; size_t tasks_cap = 0;
+  unsigned long long *d_terms = nullptr;
+  std::vector<Task> h_tasks;
+  std::vector<OutPt> h_out;
+  double *d_matrix = nullptr; size_t matrix_cap = 0;
+  PermState perm;
+  fscl_stats_t stats{};
+};
+
+int ensure_tasks(Ctx *c, size_t n) {
+  if (n <= c->tasks_cap) return FSCL_OK;
+  size_t cap = std::max<size_t>(n, c->tasks_cap * 2);
+  if (c->d_tasks) cudaFree(c->d_tasks);
+  if (c->d_out) cudaFree(c->d_out);
+  c->d_tasks = nullptr; c->d_out = nullptr; c->tasks_cap = 0;
+  CK(cudaMalloc(&c->d_tasks, cap * sizeof(Task)));
+  CK(cudaMalloc(&c->d_out, cap * sizeof(OutPt)));
+  c->tasks_cap = cap;
+  return FSCL_OK;
+}
+
+int ensure_slots(Ctx *c, int slots) {
+  if (slots <= c->max_slots) return FSCL_OK;
+  if (c->d_pcls) cudaFree(c->d_pcls);
+  if (c->d_scratch) cudaFree(c->d_scratch);
+  if (c->d_blkoff) cudaFree(c->d_blkoff);
+  c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
+  CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
+  CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
+  CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
+  c->max_slots = slots;
+  return FSCL_OK;
+}
+
+// run the scan kernel over c->h_tasks; results land in c->h_out
+int run_tasks(Ctx *c, const int *d_cls_all, int flags, bool fetch = true, double *d_clr = nullptr) {
+  size_t nt = c->h_tasks.size();
+  if (nt == 0) { c->h_out.clear(); return FSCL_OK; }
+  int rc = ensure_tasks(c, nt);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(c->ev0, c->stream));
+  launch_scan(c->P, c->d_tasks, c->d_out, d_cls_all, (int)nt, flags, c->d_terms, d_clr, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev1, c->stream));
+  if (fetch) {
+    c->h_out.resize(nt);
+    CK(cudaMemcpyAsync(c->h_out.data(), c->d_out, nt * sizeof(OutPt), cudaMemcpyDeviceToHost, c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->stats.score_kernel_ms += ms;
+  c->stats.score_launches++;
+  c->stats.n_tasks += (int64_t)nt;
+  return FSCL_OK;
+}
+
+void to_pt(const OutPt &o, fscl_pt_t &p) {
+  p.chr = o.chr; p.nearest_snp = o.nearest; p.sweep_pos = o.sweep_pos; p.n_snps = o.n_snps;
+  p.window_start = o.wstart; p.window_end = o.wend; p.lalpha = o.lalpha; p.clr = o.clr;
+  p.null_logl = o.null_logl; p.sm_logl = o.null_logl + 0.5 * o.clr;
+  p.permute_n = p.permute_p = p.permute_finished = 0; p.reserved = 0;
+}
+
+int enum_cells(const Ctx *c, int G, std::vector<Task> *out) {
+  // scan_thread's dispenser, scan-chromosome.c:178-205
+  int chm = 0, n = 0;
+  if (c->n_chr == 0) return 0;
+  int pos = c->chr_startpos[0];
+  for (;;) {
+    if (chm == c->n_chr) break;
+    if (pos >= c->chr_bplen[chm]) {
+      chm++;
+      if (chm == c->n_chr) break;
+      pos = c->chr_startpos[chm];
+    }
+    int s = pos, e = pos + G;
+    pos += G;
+    if (e > c->chr_bplen[chm]) e = c->chr_bplen[chm];
+    if (out) out->push_back(Task{0, chm, s, e, 0});
+    n++;
+  }
+  return n;
+}
+
+// Draw phase of snp_block_permute (scan-chromosome.c:345-363).  Emits
+// (i, j, len) with len = number of swaps the reference's loop :365 performs.
+// D7 (k > n_snps; the reference then indexes below the array) is DEFINED as
+// "shift the block so that it ends at n_snps" and counted.
+struct BlockGen {
+  const Ctx *c;
+  double nbp, width_bp;
+  int generate(DrawSource &src, std::vector<int4> &out, int *d7) const {
+    const int n = c->n;
+    const int *pos = c->h_pos.data();
+    int i = 0, nb = 0;
+    while (i < n) {
+      int j = (int)(src.block_draw() / (2147483647 + 1.0) * n);
+      double len = -1.0 / nbp * std::log(src.block_draw() / (2147483647 + 1.0));
+      int k = j + (len < 2147483647.0 ? (int)len : 0x3FFFFFFF);
+      if (k < n && k >= 0) {
+        // while (k < n && chr[k]==chr[j] && pos[k]-pos[j] < width) k++  -- monotone, so search
+        int lim = c->chr_end_index[j];
+        if (k < lim) {
+          int lo = k, hi = lim;              // first index in [k, lim] failing pos[.]-pos[j] < width
+          while (lo < hi) {
+            int m = lo + (hi - lo) / 2;
+            if ((double)(pos[m] - pos[j]) < width_bp) lo = m + 1; else hi = m;
+          }
+          k = lo;
+        }
+      }
+      if (i + (k - j) >= n) k = n;
+      if (k > n) { j = n - (k - j); k = n; if (d7) (*d7)++; }
+      int L = std::min(k - j, n - i);
+      if (L > 0) { out.push_back(make_int4(i, j, L, 0)); nb++; i += L; }
+    }
+    return nb;
+  }
+};
+
+}  // namespace
+
+// --------------------------------------------------------------------------- create / destroy
+static void build_alpha_tables(const double *T, AlphaTables &A) {
+  auto logt = [&](long d) -> double {
+    if (d > 0xFFFFFF) return 11.783502069519070 + T[d >> 16];
+    if (d > 0xFFFF) return 5.545177444479562 + T[d >> 8];
+    return T[d];
+  };
+  auto dmax = [&](double la) -> int {
+    if (logt(0) + la > 4.0) return -1;
+    long lo = 0, hi = 0x7FFFFFFFL;
+    if (!(logt(hi) + la > 4.0)) return (int)hi;
+    while (hi - lo > 1) { long m = (lo + hi) / 2; if (logt(m) + la > 4.0) hi = m; else lo = m; }
+    return (int)lo;
+  };
+  memset(&A, 0, sizeof A);
+  // coarse list: FP-accumulated exactly as sm-search.c:276-279
+  double step = (4.0 - (-20.0)) / 10.0;
+  int nc = 0;
+  for (double la = -20.0; la <= 4.0; la += step) {
+    if (nc < kMaxFine) { A.la[kCoarse][nc] = la; A.dmax[kCoarse][nc] = dmax(la); }
+    nc++;
+  }
+  A.n[kCoarse] = std::min(nc, kCoarse);
+  for (int m = 0; m < kCoarse; m++) {                 // sm-search.c:284-296
+    double l = A.la[kCoarse][m] - step; if (l < -20.0) l = -20.0;
+    double r = A.la[kCoarse][m] + step; if (r > 4.0) r = 4.0;
+    double s = (r - l) / 15.;
+    int k = 0;
+    for (double la = l + s; la < r; la += s) {
+      if (k < kMaxFine) { A.la[m][k] = la; A.dmax[m][k] = dmax(la); }
+      k++;
+    }
+    A.n[m] = std::min(k, kMaxFine);
+  }
+}
+
+extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
+  if (!p || !ctx_out) return fail(FSCL_ERR_ARG, "null argument");
+  *ctx_out = nullptr;
+  int ndev = fscl_device_count();
+  if (ndev <= 0) return fail(FSCL_ERR_NODEVICE, "no CUDA device: fscl_b200 has no CPU path");
+  if (p->device < 0 || p->device >= ndev) return fail(FSCL_ERR_ARG, "bad device ordinal");
+  if (p->n_snps <= 0 || p->n_chr <= 0 || p->n_cls <= 0 || p->n_knots <= 0)
+    return fail(FSCL_ERR_ARG, "empty problem");
+  CK(cudaSetDevice(p->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, p->device));
+  if (prop.major < 10) return fail(FSCL_ERR_NODEVICE, "device is not sm_100 class");
+  Ctx *c = new Ctx();
+  c->device = p->device;
+  c->n = p->n_snps; c->n_chr = p->n_chr; c->n_cls = p->n_cls;
+  c->h_chr.assign(p->chr, p->chr + c->n);
+  c->h_pos.assign(p->pos, p->pos + c->n);
+  c->h_cls.assign(p->cls, p->cls + c->n);
+  c->chr_start.assign(p->chr_start, p->chr_start + c->n_chr);
+  c->chr_nsnps.assign(p->chr_nsnps, p->chr_nsnps + c->n_chr);
+  c->chr_startpos.assign(p->chr_startpos, p->chr_startpos + c->n_chr);
+  c->chr_bplen.assign(p->chr_bplen, p->chr_bplen + c->n_chr);
+  for (int i = 0; i < c->n; i++)
+    if (c->h_cls[i] < 0 || c->h_cls[i] >= c->n_cls) { delete c; return fail(FSCL_ERR_ARG, "class index out of range"); }
+  c->chr_end_index.resize(c->n);
+  for (int i = c->n - 1; i >= 0; i--)
+    c->chr_end_index[i] = (i == c->n - 1 || c->h_chr[i + 1] != c->h_chr[i]) ? i + 1 : c->chr_end_index[i + 1];
+
+  std::vector<double> T(65536);
+  if (p->log_table) memcpy(T.data(), p->log_table, sizeof(double) * 65536);
+  else { T[0] = 0.0; for (int i = 1; i <= 0xFFFF; i++) T[i] = std::log((double)i); }   // sm-search.c:14-26
+  AlphaTables A;
+  build_alpha_tables(T.data(), A);
+
+  // knot-major table with the null model folded into c3
+  const int K = p->n_knots, NC = p->n_cls;
+  std::vector<double> coefK((size_t)K * NC * 4);
+  for (int cl = 0; cl < NC; cl++)
+    for (int k = 0; k < K; k++) {
+      const double *s = p->coef + ((size_t)cl * K + k) * 4;
+      double *d = coefK.data() + ((size_t)k * NC + cl) * 4;
+      d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3] - p->null_tab[cl];
+    }
+
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  CK(cudaMalloc(&c->d_pos, sizeof(int) * c->n));
+  CK(cudaMalloc(&c->d_cls0, sizeof(int) * c->n));
+  CK(cudaMalloc(&c->d_chr_start, sizeof(int) * c->n_chr));
+  CK(cudaMalloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
+  CK(cudaMalloc(&c->d_coefK, sizeof(double) * coefK.size()));
+  CK(cudaMalloc(&c->d_logT, sizeof(double) * 65536));
+  CK(cudaMalloc(&c->d_null, sizeof(double) * NC));
+  CK(cudaMalloc(&c->d_terms, sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_terms, 0, sizeof(unsigned long long)));
+  CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_chr_start, c->chr_start.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_chr_nsnps, c->chr_nsnps.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_coefK, coefK.data(), sizeof(double) * coefK.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_logT, T.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_null, p->null_tab, sizeof(double) * NC, cudaMemcpyHostToDevice));
+  upload_alpha_tables(A);
+  CK(cudaGetLastError());
+
+  Params &P = c->P;
+  P.n_snps = c->n; P.n_chr = c->n_chr; P.n_cls = NC; P.n_knots = K;
+  P.eval_range = p->eval_range; P.bp_resl = p->bp_resl;
+  P.inv_step = 1.0 / p->step; P.off = 20.0 / p->step;
+  P.pos = c->d_pos; P.chr_start = c->d_chr_start; P.chr_nsnps = c->d_chr_nsnps;
+  P.coefK = c->d_coefK; P.logT = c->d_logT; P.null_tab = c->d_null;
+  *ctx_out = c;
+  return FSCL_OK;
+}
+
+extern "C" void fscl_destroy(void *ctx) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_pos); cudaFree(c->d_cls0); cudaFree(c->d_chr_start); cudaFree(c->d_chr_nsnps);
+  cudaFree(c->d_coefK); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
+  cudaFree(c->d_pcls); cudaFree(c->d_scratch); cudaFree(c->d_blocks); cudaFree(c->d_blkoff);
+  cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_matrix);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+// --------------------------------------------------------------------------- forward scan
+extern "C" int fscl_enum_cells(void *ctx, int G, int32_t *cell_chr, int32_t *cell_start, int32_t *cell_end,
+                               int cap) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || G <= 0) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  std::vector<Task> cells;
+  int n = enum_cells(c, G, &cells);
+  for (int i = 0; i < n && i < cap; i++) {
+    if (cell_chr) cell_chr[i] = cells[i].chr;
+    if (cell_start) cell_start[i] = cells[i].start_pos;
+    if (cell_end) cell_end[i] = cells[i].end_pos;
+  }
+  return n;
+}
+
+static int eval_list(Ctx *c, int n, const int32_t *chr, const int32_t *start, const int32_t *end,
+                     fscl_pt_t *out, int flags) {
+  if (!c || n < 0 || (n > 0 && (!chr || !start || !out))) return fail(FSCL_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  c->h_tasks.resize(n);
+  for (int i = 0; i < n; i++) {
+    if (chr[i] < 0 || chr[i] >= c->n_chr) return fail(FSCL_ERR_ARG, "chromosome index out of range");
+    c->h_tasks[i] = Task{0, chr[i], start[i], end ? end[i] : start[i], 0};
+  }
+  int rc = run_tasks(c, c->d_cls0, flags | kFlagNullSum);
+  if (rc) return rc;
+  for (int i = 0; i < n; i++) to_pt(c->h_out[i], out[i]);
+  c->stats.n_grid_evals += n;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_grid_eval(void *ctx, int n, const int32_t *chr, const int32_t *pos, fscl_pt_t *out) {
+  return eval_list((Ctx *)ctx, n, chr, pos, nullptr, out, kFlagSingle);
+}
+
+extern "C" int fscl_search_maxpos(void *ctx, int n, const int32_t *chr, const int32_t *start_pos,
+                                  const int32_t *end_pos, fscl_pt_t *out) {
+  if (!end_pos) return fail(FSCL_ERR_ARG, "bad argument");
+  return eval_list((Ctx *)ctx, n, chr, start_pos, end_pos, out, 0);
+}
+
+extern "C" int fscl_scan_chromosome(void *ctx, int G, fscl_pt_t *out, int cap, int *n_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || G <= 0 || !out || !n_out) return fail(FSCL_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  c->h_tasks.clear();
+  int n = enum_cells(c, G, &c->h_tasks);
+  *n_out = n;
+  if (n > cap) return fail(FSCL_ERR_ARG, "output capacity too small");
+  int rc = run_tasks(c, c->d_cls0, kFlagNullSum);
+  if (rc) return rc;
+  std::vector<fscl_pt_t> pts(n);
+  for (int i = 0; i < n; i++) to_pt(c->h_out[i], pts[i]);
+  // qsort by (chr, sweep_pos), scan-chromosome.c:264 (stable here)
+  std::stable_sort(pts.begin(), pts.end(), [](const fscl_pt_t &a, const fscl_pt_t &b) {
+    return a.chr != b.chr ? a.chr < b.chr : a.sweep_pos < b.sweep_pos;
+  });
+  memcpy(out, pts.data(), sizeof(fscl_pt_t) * n);
+  return FSCL_OK;
+}
+
+// --------------------------------------------------------------------------- permutations
+static int upload_blocks(Ctx *c, const std::vector<int4> &blocks, const std::vector<int> &off) {
+  if (blocks.size() > c->blocks_cap) {
+    if (c->d_blocks) cudaFree(c->d_blocks);
+    c->d_blocks = nullptr; c->blocks_cap = 0;
+    size_t cap = blocks.size() * 2 + 1024;
+    CK(cudaMalloc(&c->d_blocks, cap * sizeof(int4)));
+    c->blocks_cap = cap;
+  }
+  if (!blocks.empty())
+    CK(cudaMemcpyAsync(c->d_blocks, blocks.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_blkoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  return FSCL_OK;
+}
+
+static int apply_blocks(Ctx *c, int n_slots) {
+  CK(cudaEventRecord(c->ev0, c->stream));
+  launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, n_slots, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev1, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+  c->stats.permute_kernel_ms += ms;
+  c->stats.permute_launches++;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_block_permute(void *ctx, const fscl_permute_opts_t *o, int t, int32_t *cls_out,
+                                  int32_t *blocks_out, int max_blocks) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !o || !cls_out || t < 0) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { fail(FSCL_ERR_CUDA, "cudaSetDevice"); return -1; }
+  if (ensure_slots(c, 1)) return -1;
+  DrawSource src;
+  src.init(o->rng_kind, o->seed);
+  BlockGen gen{c, o->permute_nbp, o->scan_width_mb * 1e6};
+  std::vector<int4> blocks;
+  int d7 = 0;
+  if (src.sequential()) {
+    if (o->rng_kind != FSCL_RNG_LIBC) (void)src.block_draw();   // usleep burn, scan-chromosome.c:440
+    for (int q = 0; q <= t; q++) { blocks.clear(); gen.generate(src, blocks, &d7); }
+  } else {
+    src.set_perm((uint32_t)t);
+    gen.generate(src, blocks, &d7);
+  }
+  std::vector<int> off = {0, (int)blocks.size()};
+  if (upload_blocks(c, blocks, off)) return -1;
+  if (apply_blocks(c, 1)) return -1;
+  if (cudaMemcpy(cls_out, c->d_pcls, sizeof(int) * c->n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    fail(FSCL_ERR_CUDA, "copy back"); return -1;
+  }
+  for (size_t b = 0; b < blocks.size() && blocks_out && (int)b < max_blocks; b++) {
+    blocks_out[3 * b] = blocks[b].x; blocks_out[3 * b + 1] = blocks[b].y; blocks_out[3 * b + 2] = blocks[b].z;
+  }
+  return (int)blocks.size();
+}
+
+// Permutation test as rounds (scan_permute_thread scan-chromosome.c:412-546).
+// A round covers permutations [t_next, t_next+R).  Each rank scores the
+// permutations t with t % stride == first into rows of a device matrix
+// clr[R][n_active] (other rows stay 0); after the caller has summed the matrix
+// over ranks (NCCL allreduce; nothing to do on one GPU) commit() replays the
+// reference's sequential counting / pruning rule over all R rows, so counts do
+// not depend on the number of GPUs.
+static int perm_begin(Ctx *c, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *o, float *permute_clr) {
+  if (!c || !o || (n_pts > 0 && !pts) || n_pts < 0 || o->large_grid_sp <= 0 || o->permute_nbp <= 0)
+    return fail(FSCL_ERR_ARG, "bad argument");
+  PermState &S = c->perm;
+  S = PermState();
+  S.o = *o;
+  S.stride = o->perm_stride > 0 ? o->perm_stride : 1;
+  if (o->first_perm < 0 || o->first_perm >= S.stride) return fail(FSCL_ERR_ARG, "first_perm out of range");
+  S.src.init(o->rng_kind, o->seed);
+  if (S.src.sequential() && S.stride != 1) return fail(FSCL_ERR_ARG, "sequential RNG streams cannot be sharded");
+  if (o->rng_kind == FSCL_RNG_GLIBC) (void)S.src.block_draw();     // usleep burn, scan-chromosome.c:440
+  if (o->rng_kind == FSCL_RNG_LIBC) (void)rand();
+  S.pts = pts; S.n_pts = n_pts; S.permute_clr = permute_clr;
+  S.active.resize(n_pts);
+  for (int i = 0; i < n_pts; i++) S.active[i] = i;
+  S.t_next = 0;
+  S.open = true;
+  return FSCL_OK;
+}
+
+// returns FSCL_OK and *R_out == 0 when the test is finished
+static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, int *n_active_out) {
+  PermState &S = c->perm;
+  if (!S.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
+  CK(cudaSetDevice(c->device));
+  const fscl_permute_opts_t &o = S.o;
+  const int G = o.large_grid_sp;
+  fscl_pt_t *pts = S.pts;
+  // compact (scan-chromosome.c:446-457)
+  size_t k = 0;
+  for (size_t a = 0; a < S.active.size(); a++)
+    if (!pts[S.active[a]].permute_finished) S.active[k++] = S.active[a];
+  S.active.resize(k);
+  *R_out = 0;
+  if (n_active_out) *n_active_out = (int)S.active.size();
+  if (S.active.empty() || S.t_next > o.n_permute) return FSCL_OK;        // D5: 0..n_permute inclusive
+  const size_t na = S.active.size();
+  int R;
+  if (S.src.sequential()) {
+    // block draws of permutation t+1 follow the pruning draws of t in the one
+    // stream; a pruning draw needs permute_p >= 20, so 20 - max_p permutations
+    // can be generated ahead without reordering the stream
+    int maxp = 0;
+    for (int s : S.active) maxp = std::max(maxp, pts[s].permute_p);
+    R = o.prune ? std::max(1, FSCL_PRUNE_MIN_P - maxp) : 64;
+  } else {
+    R = o.round_perms > 0 ? o.round_perms
+                          : (int)std::min<size_t>(256, std::max<size_t>(S.stride, (16384 + na - 1) / na));
+    R = (R + S.stride - 1) / S.stride * S.stride;
+  }
+  const size_t slot_bytes = (size_t)c->n * 8;
+  const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);
+  R = std::min(R, mem_cap * S.stride);
+  R = std::min(R, o.n_permute - S.t_next + 1);
+  if (d_matrix && (int64_t)R * (int64_t)na > cap) R = (int)std::max<int64_t>(1, cap / (int64_t)na);
+  if (d_matrix && (int64_t)na > cap) return fail(FSCL_ERR_ARG, "clr matrix too small for one permutation");
+  S.my_rows.clear();
+  S.blocks.clear(); S.off.assign(1, 0);
+  int d7 = 0;
+  BlockGen gen{c, o.permute_nbp, o.scan_width_mb * 1e6};
+  for (int r = 0; r < R; r++) {
+    int t = S.t_next + r;
+    bool mine = (t % S.stride) == o.first_perm;
+    if (S.src.sequential()) gen.generate(S.src, S.blocks, &d7);
+    else if (mine) { S.src.set_perm((uint32_t)t); gen.generate(S.src, S.blocks, &d7); }
+    if (mine) { S.my_rows.push_back(r); S.off.push_back((int)S.blocks.size()); }
+  }
+  c->stats.d7_hits += d7;
+  const int ns = (int)S.my_rows.size();
+  // matrix
+  double *dm = d_matrix;
+  if (!dm) {
+    size_t need = (size_t)R * na;
+    if (need > c->matrix_cap) {
+      if (c->d_matrix) cudaFree(c->d_matrix);
+      c->d_matrix = nullptr; c->matrix_cap = 0;
+      CK(cudaMalloc(&c->d_matrix, need * sizeof(double)));
+      c->matrix_cap = need;
+    }
+    dm = c->d_matrix;
+  }
+  S.d_matrix = dm;
+  if (ns < R) CK(cudaMemsetAsync(dm, 0, (size_t)R * na * sizeof(double), c->stream));
+  if (ns > 0) {
+    int rc = ensure_slots(c, ns); if (rc) return rc;
+    rc = upload_blocks(c, S.blocks, S.off); if (rc) return rc;
+    rc = apply_blocks(c, ns); if (rc) return rc;
+    c->stats.n_blocks += (int64_t)S.blocks.size();
+    c->h_tasks.resize((size_t)ns * na);
+    for (int q = 0; q < ns; q++)
+      for (size_t a = 0; a < na; a++) {
+        const fscl_pt_t &p = pts[S.active[a]];
+        int start = p.sweep_pos - (p.sweep_pos % G);                    // D4
+        c->h_tasks[(size_t)q * na + a] = Task{q, p.chr, start, start + G, (int)((size_t)S.my_rows[q] * na + a)};
+      }
+    rc = run_tasks(c, c->d_pcls, 0, false, dm); if (rc) return rc;
+    c->stats.n_grid_evals += (int64_t)ns * (int64_t)na;
+  } else {
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  S.R = R;
+  *R_out = R;
+  return FSCL_OK;
+}
+
+static int perm_round_commit(Ctx *c, const double *d_matrix) {
+  PermState &S = c->perm;
+  if (!S.open || S.R <= 0) return fail(FSCL_ERR_ARG, "no scored round to commit");
+  CK(cudaSetDevice(c->device));
+  const fscl_permute_opts_t &o = S.o;
+  const size_t na = S.active.size();
+  const double *dm = d_matrix ? d_matrix : S.d_matrix;
+  S.h_matrix.resize((size_t)S.R * na);
+  CK(cudaMemcpyAsync(S.h_matrix.data(), dm, S.h_matrix.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  fscl_pt_t *pts = S.pts;
+  std::vector<char> live(na, 1);
+  for (int r = 0; r < S.R; r++) {                     // scan-chromosome.c:488-498, permutation order
+    const int t = S.t_next + r;
+    bool any = false;
+    for (size_t a = 0; a < na; a++) {
+      if (!live[a]) continue;
+      any = true;
+      fscl_pt_t &p = pts[S.active[a]];
+      const double clr = S.h_matrix[(size_t)r * na + a];
+      if (clr >= p.clr) {
+        p.permute_p++;
+        if (o.prune && p.permute_p >= FSCL_PRUNE_MIN_P) {               // D6
+          int32_t u = S.src.prune_draw((uint32_t)t, (uint32_t)S.active[a]);
+          if (p.permute_p / (double)p.permute_n >= u / (2147483647 + 1.0)) { p.permute_finished = 1; live[a] = 0; }
+        }
+      }
+      if (S.permute_clr && p.permute_n < FSCL_NULL_SAVE)
+        S.permute_clr[(size_t)S.active[a] * FSCL_NULL_SAVE + p.permute_n] = (float)clr;
+      p.permute_n++;
+    }
+    if (!any) break;
+    c->stats.n_scored++;
+  }
+  c->stats.n_rounds++;
+  S.t_next += S.R;
+  S.R = 0;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_perm_begin(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *o,
+                               float *permute_clr) {
+  return perm_begin((Ctx *)ctx, pts, n_pts, o, permute_clr);
+}
+extern "C" int fscl_perm_round_score(void *ctx, double *d_matrix, int64_t cap, int *R_out, int *n_active_out) {
+  if (!ctx || !R_out) return fail(FSCL_ERR_ARG, "bad argument");
+  return perm_round_score((Ctx *)ctx, d_matrix, cap, R_out, n_active_out);
+}
+extern "C" int fscl_perm_round_commit(void *ctx, const double *d_matrix) {
+  if (!ctx) return fail(FSCL_ERR_ARG, "bad argument");
+  return perm_round_commit((Ctx *)ctx, d_matrix);
+}
+extern "C" int fscl_perm_end(void *ctx, fscl_stats_t *stats_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  c->perm.open = false;
+  if (stats_out) *stats_out = c->stats;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *o,
+                                 float *permute_clr, fscl_stats_t *stats_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (o && o->perm_stride > 1)
+    return fail(FSCL_ERR_ARG, "sharded runs must use the round API and sum the matrix across ranks");
+  int rc = perm_begin(c, pts, n_pts, o, permute_clr);
+  if (rc) return rc;
+  for (;;) {
+    int R = 0;
+    rc = perm_round_score(c, nullptr, 0, &R, nullptr);
+    if (rc) return rc;
+    if (R == 0) break;
+    rc = perm_round_commit(c, nullptr);
+    if (rc) return rc;
+  }
+  return fscl_perm_end(c, stats_out);
+}
+
+// --------------------------------------------------------------------------- bench / stats
+extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !s) return fail(FSCL_ERR_ARG, "bad argument");
+  *s = c->stats;
+  return FSCL_OK;
+}
+extern "C" int fscl_reset_stats(void *ctx) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  memset(&c->stats, 0, sizeof c->stats);
+  return FSCL_OK;
+}
+
+// Whole permuted scans with everything resident in HBM: n_perm_slots Philox
+// permutations (t = 0..n-1, seed 1) of the observed classes are built on the
+// device and every cell of every permuted genome is searched (no pruning, so
+// scans are equal-work).  n_perm_slots == 0 scans the observed genome once.
+extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_terms, int64_t *terms_out,
+                               fscl_stats_t *stats_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || G <= 0 || n_perm_slots < 0) return fail(FSCL_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  std::vector<Task> cells;
+  enum_cells(c, G, &cells);
+  const int *d_cls = c->d_cls0;
+  int ns = 1;
+  if (n_perm_slots > 0) {
+    ns = n_perm_slots;
+    int rc = ensure_slots(c, ns); if (rc) return rc;
+    DrawSource src; src.init(FSCL_RNG_PHILOX, 1);
+    BlockGen gen{c, 0.1, 1e6};
+    std::vector<int4> blocks; std::vector<int> off(1, 0);
+    int d7 = 0;
+    for (int q = 0; q < ns; q++) { src.set_perm((uint32_t)q); gen.generate(src, blocks, &d7); off.push_back((int)blocks.size()); }
+    rc = upload_blocks(c, blocks, off); if (rc) return rc;
+    rc = apply_blocks(c, ns); if (rc) return rc;
+    c->stats.n_blocks += (int64_t)blocks.size();
+    d_cls = c->d_pcls;
+  }
+  c->h_tasks.resize((size_t)ns * cells.size());
+  for (int q = 0; q < ns; q++)
+    for (size_t a = 0; a < cells.size(); a++) {
+      Task t = cells[a]; t.slot = q;
+      if (n_perm_slots > 0) { t.start_pos = t.start_pos - (t.start_pos % G); t.end_pos = t.start_pos + G; }
+      c->h_tasks[(size_t)q * cells.size() + a] = t;
+    }
+  if (count_terms) CK(cudaMemsetAsync(c->d_terms, 0, sizeof(unsigned long long), c->stream));
+  int rc = run_tasks(c, d_cls, count_terms ? kFlagCount : 0, false);
+  if (rc) return rc;
+  if (count_terms && terms_out) {
+    unsigned long long v = 0;
+    CK(cudaMemcpy(&v, c->d_terms, sizeof v, cudaMemcpyDeviceToHost));
+    *terms_out = (int64_t)v;
+  }
+  c->stats.n_scored += ns;
+  if (stats_out) *stats_out = c->stats;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_fp64_peak(int device, double *tflops) {
+  if (!tflops) return fail(FSCL_ERR_ARG, "bad argument");
+  if (fscl_device_count() <= 0) return fail(FSCL_ERR_NODEVICE, "no CUDA device");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  int grid = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double *d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * grid * 256));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, 0));
+    launch_fma_peak(d, iters, grid, 0);
+    CK(cudaEventRecord(e1, 0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 8.0 * iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+  }
+  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  *tflops = best;
+  return FSCL_OK;
+}

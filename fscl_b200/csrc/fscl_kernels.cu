@@ -1,0 +1,285 @@
+// fscl_kernels.cu -- sm_100a kernels (see fscl_kernels.cuh for the reference map).
+#include "fscl_kernels.cuh"
+
+namespace fscl {
+
+__constant__ AlphaTables c_alpha;
+
+void upload_alpha_tables(const AlphaTables &t) { cudaMemcpyToSymbol(c_alpha, &t, sizeof(AlphaTables)); }
+
+// ---------------------------------------------------------------------------
+// logt, sm-search.c:40-46 (D2 constant kept).  d >= 0.
+__device__ __forceinline__ double dev_logt(const double *__restrict__ T, int d) {
+  int sh = d > 0xFFFFFF ? 16 : (d > 0xFFFF ? 8 : 0);
+  double c = d > 0xFFFFFF ? 11.783502069519070 : (d > 0xFFFF ? 5.545177444479562 : 0.0);
+  double t = __ldg(T + (d >> sh));
+  return sh ? c + t : t;
+}
+
+struct PtS {          // one evaluated scan point, shared by the CTA
+  int nearest, sweep_pos, wstart, wend, dnear;
+  double lalpha, clr;
+  double nsum;        // window null log-likelihood (scan-chromosome.c:92-94)
+};
+
+// init_scan_result, scan-chromosome.c:58-101 (window null sum is deferred)
+__device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
+  const int start = P.chr_start[chr], n = P.chr_nsnps[chr];
+  const int *__restrict__ p = P.pos + start;
+  // search_snppos scan-chromosome.c:39-56
+  int i = 0, j = n;
+  const double sp = (double)pos;
+  while (j - i > 1) {
+    int m = (i + j) / 2;
+    if ((double)__ldg(p + m) < sp) i = m; else j = m;
+  }
+  int nearest;
+  if (j == n) nearest = n - 1;
+  else if ((sp - (double)__ldg(p + i)) < ((double)__ldg(p + j) - sp)) nearest = i;
+  else nearest = j;
+  nearest += start;
+  // D3: global index against the per-chromosome count, literally
+  int g = nearest;
+  while (g < n && __ldg(P.pos + g) == pos) { g++; pos++; }
+  const int er = P.eval_range;
+  const int chm_start = start, chm_stop = start + n - 1;
+  int ws, we;
+  if (nearest - er < chm_start) {
+    ws = chm_start; we = chm_start + er * 2; if (we > chm_stop) we = chm_stop;
+  } else if (nearest + er > chm_stop) {
+    we = chm_stop; ws = chm_stop - er * 2; if (ws < chm_start) ws = chm_start;
+  } else { ws = nearest - er; we = nearest + er; }
+  R.nearest = nearest; R.sweep_pos = pos; R.wstart = ws; R.wend = we;
+  int d = pos - __ldg(P.pos + nearest);
+  R.dnear = d < 0 ? -d : d;
+}
+
+// One pass over the window for the alpha list in c_alpha row `row`:
+// S[j] = sum over window sites with d <= dmax[j] of spline_cls(logt(d)+la[j]) - null
+// (sm_likelihood sm-search.c:105-150; the walks' "break at first exceed" equals
+// the distance cut because logt is monotone; nearest failing => empty sum).
+//
+// The reference accumulates the terms onto null_logl (about -1e5..-1e6), so sums
+// below ulp(null_logl)/2 vanish and candidates tie EXACTLY (first one wins,
+// sm-search.c:281; CLR is exactly 0 in flat regions).  That is reproduced by
+// returning S[j] = (N + sum_j) - N with N the window null sum, which the coarse
+// pass (WITHN) accumulates alongside.
+template <int NA, bool COUNT, bool WITHN>
+__device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ cls, PtS &R,
+                                          int row, double (*red)[kMaxFine + 1], double *S,
+                                          unsigned long long &nterms) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int na_all = c_alpha.n[row];
+  int na = 0;                       // alphas whose cut admits the nearest site (prefix: dmax descends)
+#pragma unroll
+  for (int j = 0; j < NA; j++)
+    if (j < na_all && R.dnear <= c_alpha.dmax[row][j]) na = j + 1;
+  double acc[NA];
+  double accn = 0.0;
+#pragma unroll
+  for (int j = 0; j < NA; j++) acc[j] = 0.0;
+  if (na > 0 || WITHN) {
+    const int sweep = R.sweep_pos, ws = R.wstart, we = R.wend;
+    const int *__restrict__ gpos = P.pos;
+    const double2 *__restrict__ coef = reinterpret_cast<const double2 *>(P.coefK);
+    const int ncls = P.n_cls, kmax = P.n_knots - 1;
+    const double inv_step = P.inv_step, off = P.off;
+    for (int base = (ws & ~31) + warp * 32; base <= we; base += kScanWarps * 32) {
+      const int i = base + lane;
+      const bool valid = (i >= ws) && (i <= we);
+      int d = 0x7FFFFFFF, c = 0;
+      if (valid) {
+        d = __ldg(gpos + i) - sweep;
+        d = d < 0 ? -d : d;
+        c = __ldg(cls + i);
+      }
+      const double x0 = valid ? dev_logt(P.logT, d) : 0.0;
+      if (WITHN && valid) accn += __ldg(P.null_tab + c);
+#pragma unroll
+      for (int j = 0; j < NA; j++) {
+        if (j >= na) break;
+        const bool inc = valid && d <= c_alpha.dmax[row][j];
+        if (!__any_sync(0xFFFFFFFFu, inc)) break;
+        const double x = x0 + c_alpha.la[row][j];
+        int k = __double2int_rz(fma(x, inv_step, off));
+        k = min(max(k, 0), kmax);
+        const double2 *r = coef + ((size_t)k * ncls + c) * 2;
+        const double2 a = __ldg(r), b = __ldg(r + 1);
+        const double y = fma(x, fma(x, fma(x, a.x, a.y), b.x), b.y);
+        if (inc) acc[j] += y;
+        if (COUNT) nterms += inc ? 1ull : 0ull;
+      }
+    }
+  }
+  // fixed-tree reduction: deterministic, independent of launch shape
+#pragma unroll
+  for (int j = 0; j < NA; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  if (WITHN) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accn += __shfl_xor_sync(0xFFFFFFFFu, accn, o);
+    if (lane == 0) red[warp][kMaxFine] = accn;
+  }
+  __syncthreads();
+  if (threadIdx.x < NA) {
+    double N = R.nsum;
+    if (WITHN) {
+      N = 0.0;
+#pragma unroll
+      for (int w = 0; w < kScanWarps; w++) N += red[w][kMaxFine];
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
+    S[threadIdx.x] = (int)threadIdx.x < na ? (N + v) - N : 0.0;
+    if (WITHN && threadIdx.x == 0) S[kMaxFine] = N;
+  }
+  __syncthreads();
+  if (WITHN && threadIdx.x == 0) R.nsum = S[kMaxFine];
+}
+
+// search_maxalpha sm-search.c:269-300 at one position
+template <bool COUNT>
+__device__ void dev_eval(const Params &P, const int *__restrict__ cls, int chr, int pos, PtS &R,
+                         double (*red)[kMaxFine + 1], double *S, int *s_row, unsigned long long &nterms) {
+  if (threadIdx.x == 0) dev_init_point(P, chr, pos, R);
+  __syncthreads();
+  dev_phase<kCoarse, COUNT, true>(P, cls, R, kCoarse, red, S, nterms);
+  if (threadIdx.x == 0) {
+    // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
+    // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
+    // (scan-chromosome.c:97), whose fine interval is that of the last coarse value
+    int best = -1; double bs = -1.7976931348623157e308;
+    for (int j = 0; j < kCoarse; j++) if (S[j] > bs) { bs = S[j]; best = j; }
+    R.clr = bs; R.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
+    *s_row = best < 0 ? kCoarse - 1 : best;
+  }
+  __syncthreads();
+  const int row = *s_row;
+  dev_phase<kMaxFine, COUNT, false>(P, cls, R, row, red, S, nterms);
+  if (threadIdx.x == 0) {
+    double bs = R.clr, la = R.lalpha;
+    const int nf = c_alpha.n[row];
+    for (int j = 0; j < nf; j++) if (S[j] > bs) { bs = S[j]; la = c_alpha.la[row][j]; }
+    R.lalpha = la; R.clr = 2.0 * bs;                // sm-search.c:298 without the null cancellation
+  }
+  __syncthreads();
+}
+
+// search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell)
+template <bool COUNT>
+__global__ void __launch_bounds__(kScanThreads, 4)
+scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tasks, OutPt *__restrict__ out,
+                  const int *__restrict__ cls_all, int flags, unsigned long long *term_counter,
+                  double *__restrict__ clr_matrix) {
+  __shared__ PtS A, B, M;
+  __shared__ double red[kScanWarps][kMaxFine + 1];
+  __shared__ double S[kMaxFine + 1];
+  __shared__ int s_row, s_go;
+  const Task t = tasks[blockIdx.x];
+  const int *__restrict__ cls = cls_all + (size_t)t.slot * P.n_snps;
+  unsigned long long nterms = 0;
+
+  dev_eval<COUNT>(P, cls, t.chr, t.start_pos, A, red, S, &s_row, nterms);
+  if (!(flags & kFlagSingle)) {
+    dev_eval<COUNT>(P, cls, t.chr, t.end_pos, B, red, S, &s_row, nterms);
+    for (;;) {
+      if (threadIdx.x == 0) s_go = (B.sweep_pos - A.sweep_pos > P.bp_resl);
+      __syncthreads();
+      if (!s_go) break;
+      dev_eval<COUNT>(P, cls, t.chr, (A.sweep_pos + B.sweep_pos) / 2, M, red, S, &s_row, nterms);
+      if (threadIdx.x == 0) {
+        if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M; else A = M;   // scan-chromosome.c:116
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && !(A.clr > B.clr)) A = B;                  // scan-chromosome.c:110
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    OutPt o;
+    o.chr = t.chr; o.nearest = A.nearest; o.sweep_pos = A.sweep_pos;
+    o.n_snps = A.wend - A.wstart + 1; o.wstart = A.wstart; o.wend = A.wend;
+    o.lalpha = A.lalpha; o.clr = A.clr; o.null_logl = A.nsum;
+    out[blockIdx.x] = o;
+    if (clr_matrix) clr_matrix[t.dst] = A.clr;
+  }
+  if (COUNT) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nterms += __shfl_xor_sync(0xFFFFFFFFu, nterms, o);
+    if ((threadIdx.x & 31) == 0 && nterms) atomicAdd(term_counter, nterms);
+  }
+}
+
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *cls_all, int n_tasks,
+                 int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
+  if (n_tasks <= 0) return;
+  if (flags & kFlagCount)
+    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, cls_all, flags, term_counter, clr_matrix);
+  else
+    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, cls_all, flags, term_counter, clr_matrix);
+}
+
+// ---------------------------------------------------------------------------
+// Swap phase of snp_block_permute (scan-chromosome.c:365-384): one CTA per
+// permutation slot applies its block list IN ORDER; elements of a block move in
+// parallel.  Self-overlapping blocks (|i-j| < len) are a chained swap in the
+// reference; its closed form is: new[a+t] = old[a+t+delta] for t < len and the
+// first delta originals land at a + r + delta*ceil((len-r)/delta).
+__global__ void __launch_bounds__(kPermThreads)
+permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, int *__restrict__ scratch_all,
+               const int4 *__restrict__ blocks, const int *__restrict__ blk_off) {
+  const int slot = blockIdx.x;
+  int *pc = pcls_all + (size_t)slot * n;
+  int *sc = scratch_all + (size_t)slot * n;
+  for (int i = threadIdx.x; i < n; i += kPermThreads) pc[i] = cls0[i];
+  __syncthreads();
+  const int b0 = blk_off[slot], b1 = blk_off[slot + 1];
+  for (int b = b0; b < b1; b++) {
+    const int4 blk = blocks[b];
+    const int i = blk.x, j = blk.y, L = blk.z;
+    const int a = min(i, j), delta = max(i, j) - a;
+    if (delta == 0 || L <= 0) continue;
+    if (delta >= L) {
+      for (int t = threadIdx.x; t < L; t += kPermThreads) {
+        int u = pc[i + t], v = pc[j + t];
+        pc[i + t] = v; pc[j + t] = u;
+      }
+    } else {
+      for (int t = threadIdx.x; t < L + delta; t += kPermThreads) sc[t] = pc[a + t];
+      __syncthreads();
+      for (int t = threadIdx.x; t < L; t += kPermThreads) pc[a + t] = sc[t + delta];
+      for (int r = threadIdx.x; r < delta; r += kPermThreads)
+        pc[a + r + delta * ((L - r + delta - 1) / delta)] = sc[r];
+    }
+    __syncthreads();
+  }
+}
+
+void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
+                    const int *blk_off, int n_slots, cudaStream_t s) {
+  if (n_slots <= 0) return;
+  permute_kernel<<<n_slots, kPermThreads, 0, s>>>(n, cls0, pcls_all, scratch_all, blocks, blk_off);
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA peak: 8 independent dependent-chains per thread.
+__global__ void __launch_bounds__(256) fma_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s) {
+  fma_peak_kernel<<<grid, 256, 0, s>>>(out, iters);
+}
+
+}  // namespace fscl

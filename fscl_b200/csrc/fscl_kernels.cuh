@@ -1,0 +1,65 @@
+// fscl_kernels.cuh -- device side of the CLR scan + block permutation (sm_100a).
+//
+// Path replaced (reference slowkoni/fscl, cited file:line):
+//   logt                    sm-search.c:40-46
+//   spline_interpolate      sm-spline.c:48-60
+//   snp_likelihood          sm-search.c:85-103
+//   sm_likelihood           sm-search.c:105-150
+//   search_maxalpha         sm-search.c:269-300
+//   init_scan_result        scan-chromosome.c:58-101
+//   search_maxpos(_rec.)    scan-chromosome.c:103-139
+//   snp_block_permute       scan-chromosome.c:336-389 (swap phase)
+//
+// Not a dense contraction: the bound is the FP64 FMA pipe fed by 32-byte
+// coefficient gathers that stay in L1/L2; tensor cores are deliberately unused.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fscl {
+
+constexpr int kCoarse = 11;      // coarse alpha candidates (sm-search.c:276-282)
+constexpr int kMaxFine = 15;     // fine alpha candidates   (sm-search.c:284-296)
+constexpr int kRows = kCoarse + 1;  // fine lists for each coarse argmax + the coarse list (row 11)
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kPermThreads = 1024;
+
+struct Params {
+  int n_snps, n_chr, n_cls, n_knots, eval_range, bp_resl;
+  double inv_step, off;            // knot = trunc(x * inv_step + off), off = 20 / step
+  const int *pos;                  // [n_snps]
+  const int *chr_start, *chr_nsnps;
+  const double *coefK;             // [n_knots][n_cls][4], c3 already minus null_tab[cls]
+  const double *logT;              // [65536]
+  const double *null_tab;          // [n_cls]
+};
+
+struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix
+
+struct OutPt {
+  int chr, nearest, sweep_pos, n_snps, wstart, wend;
+  double lalpha, clr, null_logl;
+};
+
+// alpha candidate tables, identical for every problem (depend on the LUT only):
+// row 11 = coarse list; row m<11 = fine list when the coarse argmax is m.
+struct AlphaTables {
+  double la[kRows][kMaxFine];
+  int dmax[kRows][kMaxFine];     // largest distance with !(logt(d)+la > 4); -1 if none
+  int n[kRows];
+};
+
+void upload_alpha_tables(const AlphaTables &t);
+
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *cls_all, int n_tasks,
+                 int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
+void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
+                    const int *blk_off, int n_slots, cudaStream_t s);
+void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);
+
+enum { kFlagSingle = 1,      // evaluate start_pos only (search_maxalpha at a point)
+       kFlagNullSum = 2,     // also sum null_tab over the final window
+       kFlagCount = 4 };     // count SNP-terms (roofline numerator)
+
+}  // namespace fscl

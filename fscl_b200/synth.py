@@ -70,8 +70,13 @@ def config2(seed=102, scale=1.0, planted=True):
                              planted=planted), dict(G=100_000, p=1000)
 
 
-def config3(seed=103, scale=1.0, n_chr=2):
-    """Array-style: variable depth, K=2 of M=20 ascertainment, 30 % folded."""
+def config3(seed=103, scale=1.0, n_chr=2, depths=(98, 88, 86, 82, 78)):
+    """Array-style: variable depth, K=2 of M=20 ascertainment, 30 % folded.
+
+    The default depths are ones for which the reference's ascertainment
+    probability of a singleton (asc-bias.c:12-25: 1 - C(n,20)/C(n,20), pure
+    rounding noise) comes out positive; for depths where it comes out negative
+    (e.g. 100, 96, 94, 90) the reference's tables are NaN."""
     rng = np.random.Generator(np.random.PCG64(seed))
     n_sites = max(int(100_000 * scale), 200)
     length = max(int(100_000_000 * scale), 20_000)
@@ -82,7 +87,7 @@ def config3(seed=103, scale=1.0, n_chr=2):
         pos.append(_positions(rng, m, length // n_chr))
         chr_of.append(np.full(m, c))
     chr_of, pos = np.concatenate(chr_of), np.concatenate(pos)
-    depth = rng.choice([100, 98, 96, 94, 90], size=n_sites, p=[0.6, 0.1, 0.1, 0.1, 0.1])
+    depth = rng.choice(list(depths), size=n_sites, p=[0.6, 0.1, 0.1, 0.1, 0.1])
     cnt = _neutral_counts(rng, n_sites, depth)
     bad = (cnt < 2) | (cnt > depth - 2)
     while bad.any():

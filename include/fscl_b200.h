@@ -1,0 +1,145 @@
+/* fscl_b200.h -- C-ABI of the B200-native CLR sweep scan + block-permutation test.
+ *
+ * This library replaces the hot path of slowkoni/fscl (reference tree cited as
+ * file:line below).  The reference has no plugin/FFI layer; its boundary is the
+ * internal C API of fscl.h:103-116 called from main() (fscl.c:316-335).  Two
+ * layers are exported:
+ *
+ *  1. fscl_*  (this header): plain pointers + sizes, flattened tables.  Host
+ *     buffers in, host buffers out; all device memory is owned by fscl_ctx.
+ *  2. the reference's own entry points with the reference's struct layouts
+ *     (include/fscl_dropin.h, libfscl_dropin.so), implemented on top of 1.
+ *
+ * There is no CPU fallback: every entry point fails (non-zero return,
+ * fscl_last_error()) when no sm_100 device is usable.
+ */
+#ifndef FSCL_B200_H
+#define FSCL_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSCL_OK 0
+#define FSCL_ERR_CUDA 1
+#define FSCL_ERR_ARG 2
+#define FSCL_ERR_NODEVICE 3
+
+#define FSCL_NULL_SAVE 10000          /* CLR_NULL_DIST_SAVE scan-chromosome.c:227 */
+#define FSCL_PRUNE_MIN_P 20           /* scan-chromosome.c:490 */
+
+/* Flattened problem.  A site's "class" selects one spline of the sweep-model
+ * table: (depth_p, folded, obs_freq) -> sm_p[depth_p].(f)spline_func[obs_freq]
+ * (sm-search.c:92-100).  null_tab[cls] is snp_t.null_logl
+ * (scan-chromosome.c:23-37), a function of the class only. */
+typedef struct {
+  int32_t n_snps;
+  const int32_t *chr;          /* [n_snps] snp_t.chr  (fscl.h:8)  sorted (chr,pos) */
+  const int32_t *pos;          /* [n_snps] snp_t.pos  (fscl.h:9)                   */
+  const int32_t *cls;          /* [n_snps] class index, 0 <= cls < n_cls           */
+  int32_t n_chr;
+  const int32_t *chr_start;    /* chr_limits_t.start_index (fscl.h:29) */
+  const int32_t *chr_nsnps;    /* chr_limits_t.n_snps      (fscl.h:30) */
+  const int32_t *chr_startpos; /* chr_limits_t.start_pos   (fscl.h:31) */
+  const int32_t *chr_bplen;    /* chr_limits_t.bp_length   (fscl.h:32) */
+  int32_t n_cls;
+  int32_t n_knots;             /* spline_t.n (fscl.h:65) = --splines */
+  double step;                 /* log_ad_step sm-spline.c:325 */
+  const double *coef;          /* [n_cls][n_knots][4]  spline_t.coef (fscl.h:67) */
+  const double *null_tab;      /* [n_cls] */
+  const double *log_table;     /* [65536] init_log_table sm-search.c:14-26, or NULL: built with libm */
+  int32_t eval_range;          /* 81920  fscl.c:175 */
+  int32_t bp_resl;             /* 128    fscl.c:174 */
+  int32_t device;              /* CUDA device ordinal */
+  int32_t max_round_perms;     /* 0 = default; permutation slots resident at once */
+} fscl_problem_t;
+
+/* One scan point; field meaning = scan_pt_t fscl.h:35-51 (without the
+ * permute_clr pointer and scan_running). sm_logl/null_logl are filled by the
+ * forward scan only. clr = 2 * sum of per-site log-likelihood differences
+ * (sm-search.c:298 evaluated without the null_logl cancellation). */
+typedef struct {
+  int32_t chr, nearest_snp, sweep_pos, n_snps, window_start, window_end;
+  double lalpha, null_logl, sm_logl, clr;
+  int32_t permute_n, permute_p, permute_finished, reserved;
+} fscl_pt_t;
+
+enum { FSCL_RNG_GLIBC = 0,   /* own restatement of glibc TYPE_3 rand(), seeded by .seed */
+       FSCL_RNG_PHILOX = 1,  /* Philox4x32-10 keyed by .seed, counter (idx, stream, t, 0) */
+       FSCL_RNG_LIBC = 2 };  /* the process's libc rand() (drop-in: stream seeded at fscl.c:135) */
+
+typedef struct {
+  int32_t n_permute;        /* scores n_permute+1 permutations (scan-chromosome.c:444,466) */
+  double permute_nbp;       /* --permute-nbp */
+  int32_t large_grid_sp;    /* -G */
+  double scan_width_mb;     /* -w */
+  int32_t rng_kind;
+  uint64_t seed;
+  int32_t prune;            /* 1 = stochastic pruning as scan-chromosome.c:488-494; 0 = score everything */
+  int32_t first_perm;       /* sharding: score permutations t with t % perm_stride == first_perm */
+  int32_t perm_stride;      /* 1 on a single GPU */
+  int32_t round_perms;      /* 0 = auto */
+} fscl_permute_opts_t;
+
+typedef struct {
+  int64_t n_scored;         /* permutations scored                         */
+  int64_t n_tasks;          /* (permutation, cell) searches launched       */
+  int64_t n_grid_evals;     /* search_maxalpha calls                       */
+  int64_t n_rounds;
+  int64_t n_blocks;         /* permutation blocks applied                  */
+  int32_t d7_hits;          /* blocks that overshot the array end (defined behaviour) */
+  int32_t reserved;
+  double score_kernel_ms;   /* CUDA-event time of the scan kernel, summed  */
+  double permute_kernel_ms; /* CUDA-event time of the block-permute kernel */
+  int64_t score_launches, permute_launches;
+} fscl_stats_t;
+
+const char *fscl_last_error(void);
+int fscl_device_count(void);
+
+int  fscl_create(const fscl_problem_t *p, void **ctx_out);
+void fscl_destroy(void *ctx);
+
+/* cell enumeration of scan_thread (scan-chromosome.c:178-205); returns the count */
+int fscl_enum_cells(void *ctx, int large_grid_sp, int32_t *cell_chr, int32_t *cell_start,
+                    int32_t *cell_end, int cap);
+/* init_scan_result + search_maxalpha at n given positions (scan-chromosome.c:58, sm-search.c:269) */
+int fscl_grid_eval(void *ctx, int n, const int32_t *chr, const int32_t *pos, fscl_pt_t *out);
+/* search_maxpos over n cells (scan-chromosome.c:126) on the observed classes */
+int fscl_search_maxpos(void *ctx, int n, const int32_t *chr, const int32_t *start_pos,
+                       const int32_t *end_pos, fscl_pt_t *out);
+/* scan_chromosome (scan-chromosome.c:228): all cells, sorted by (chr, sweep_pos) */
+int fscl_scan_chromosome(void *ctx, int large_grid_sp, fscl_pt_t *out, int cap, int *n_out);
+/* snp_block_permute (scan-chromosome.c:336) for permutation index t of the
+ * stream described by opts; writes the permuted classes and, if blocks != NULL,
+ * up to max_blocks (i, j, len) triples. Returns #blocks or <0. Test hook. */
+int fscl_block_permute(void *ctx, const fscl_permute_opts_t *opts, int t, int32_t *cls_out,
+                       int32_t *blocks, int max_blocks);
+/* scan_permute (scan-chromosome.c:582): pts in/out (permute_p/n/finished updated);
+ * permute_clr = [n_pts][FSCL_NULL_SAVE] floats or NULL */
+int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *opts,
+                      float *permute_clr, fscl_stats_t *stats);
+/* The same test as rounds, for sharding permutations over GPUs:
+ *   begin; loop { round_score -> [caller: allreduce(sum) of the matrix over ranks]
+ *                 -> round_commit } until *R_out == 0; end.
+ * Rank g of n sets opts->first_perm = g, opts->perm_stride = n (Philox only).
+ * d_matrix is a DEVICE buffer of cap doubles laid out [R][n_active] (rows of
+ * other ranks are zero-filled) or NULL to use an internal one (single GPU).
+ * pts / permute_clr must stay valid until fscl_perm_end. */
+int fscl_perm_begin(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *opts,
+                    float *permute_clr);
+int fscl_perm_round_score(void *ctx, double *d_matrix, int64_t cap, int *R_out, int *n_active_out);
+int fscl_perm_round_commit(void *ctx, const double *d_matrix);
+int fscl_perm_end(void *ctx, fscl_stats_t *stats);
+/* device-resident variants used by bench.py: time whole scans with inputs in HBM */
+int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_terms,
+                    int64_t *terms_out, fscl_stats_t *stats);
+int fscl_get_stats(void *ctx, fscl_stats_t *stats);
+int fscl_reset_stats(void *ctx);
+/* FP64 FMA peak of the device (dependent-chain microbenchmark), in TFLOP/s */
+int fscl_fp64_peak(int device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

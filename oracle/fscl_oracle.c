@@ -113,6 +113,10 @@ void fo_sm_likelihood(const fo_ctx_t *c, const int *cls, fo_pt_t *pt) {
       s += term(c, cls[i], log_ad);
     }
     pt->sm_logl = (double)s;
+    if (c->mode == 2) {      /* absorb into the null sum the way the reference's accumulator does */
+      volatile double t = pt->null_logl + (double)s;
+      pt->sm_logl = t - pt->null_logl;
+    }
   }
 }
 

@@ -50,7 +50,11 @@ typedef struct {
   int bp_resl;            /* 128   */
   int mode;               /* 0: reference arithmetic (sm_logl = null + sum, sequential)
                              1: delta arithmetic (long-double sum of the per-site terms,
-                                sm_logl := that sum, clr = 2*sum) */
+                                sm_logl := that sum, clr = 2*sum)
+                             2: as 1, then quantised to the reference accumulator's grid:
+                                sm_logl := (null_logl + sum) - null_logl, so that sums below
+                                ulp(null_logl)/2 tie exactly as they do in the reference.
+                                This is the arithmetic the CUDA path implements. */
 } fo_ctx_t;
 
 typedef struct {

@@ -133,9 +133,14 @@ struct Ctx {
   std::vector<int> chr_end_index;         // per SNP: one past the last index of its chromosome
   // device
   int *d_pos = nullptr, *d_cls0 = nullptr, *d_chr_start = nullptr, *d_chr_nsnps = nullptr;
-  double *d_coefK = nullptr, *d_logT = nullptr, *d_null = nullptr;
+  double *d_coefC = nullptr, *d_logT = nullptr, *d_null = nullptr;
+  int n_pad = 0;
+  int *d_tkey0 = nullptr, *d_tpos0 = nullptr;     // observed genome, class-bucketed
+  double *d_tnull0 = nullptr, *d_tnull = nullptr; // per-tile null sums (observed / slots)
+  int *d_tile_lo = nullptr, *d_tile_hi = nullptr;
   int max_slots = 0;
   int *d_pcls = nullptr, *d_scratch = nullptr;
+  int *d_tkey = nullptr, *d_tpos = nullptr;       // permutation slots, class-bucketed
   int4 *d_blocks = nullptr; size_t blocks_cap = 0;
   int *d_blkoff = nullptr;
   Task *d_tasks = nullptr; OutPt *d_out = nullptr; size_t tasks_cap = 0;
@@ -164,7 +169,13 @@ int ensure_slots(Ctx *c, int slots) {
   if (c->d_pcls) cudaFree(c->d_pcls);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_blkoff) cudaFree(c->d_blkoff);
-  c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
+  if (c->d_tkey) cudaFree(c->d_tkey);
+  if (c->d_tpos) cudaFree(c->d_tpos);
+  if (c->d_tnull) cudaFree(c->d_tnull);
+  c->d_pcls = c->d_scratch = c->d_blkoff = c->d_tkey = c->d_tpos = nullptr; c->d_tnull = nullptr; c->max_slots = 0;
+  CK(cudaMalloc(&c->d_tnull, (size_t)slots * (c->n_pad / kTile) * sizeof(double)));
+  CK(cudaMalloc(&c->d_tkey, (size_t)slots * c->n_pad * sizeof(int)));
+  CK(cudaMalloc(&c->d_tpos, (size_t)slots * c->n_pad * sizeof(int)));
   CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
@@ -173,14 +184,15 @@ int ensure_slots(Ctx *c, int slots) {
 }
 
 // run the scan kernel over c->h_tasks; results land in c->h_out
-int run_tasks(Ctx *c, const int *d_cls_all, int flags, bool fetch = true, double *d_clr = nullptr) {
+int run_tasks(Ctx *c, bool permuted, int flags, bool fetch = true, double *d_clr = nullptr) {
   size_t nt = c->h_tasks.size();
   if (nt == 0) { c->h_out.clear(); return FSCL_OK; }
   int rc = ensure_tasks(c, nt);
   if (rc) return rc;
   CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev0, c->stream));
-  launch_scan(c->P, c->d_tasks, c->d_out, d_cls_all, (int)nt, flags, c->d_terms, d_clr, c->stream);
+  launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->d_tkey : c->d_tkey0, permuted ? c->d_tpos : c->d_tpos0,
+              permuted ? c->d_tnull : c->d_tnull0, (int)nt, flags, c->d_terms, d_clr, c->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
   if (fetch) {
@@ -272,7 +284,7 @@ static void build_alpha_tables(const double *T, AlphaTables &A) {
   auto dmax = [&](double la) -> int {
     if (logt(0) + la > 4.0) return -1;
     long lo = 0, hi = 0x7FFFFFFFL;
-    if (!(logt(hi) + la > 4.0)) return (int)hi;
+    if (!(logt(hi) + la > 4.0)) return 0x7FFFFFFE;   // capped: INT_MAX marks records outside the window
     while (hi - lo > 1) { long m = (lo + hi) / 2; if (logt(m) + la > 4.0) hi = m; else lo = m; }
     return (int)lo;
   };
@@ -332,15 +344,25 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   AlphaTables A;
   build_alpha_tables(T.data(), A);
 
-  // knot-major table with the null model folded into c3
+  // class-major table [cls][knot][4] with the null model folded into c3
   const int K = p->n_knots, NC = p->n_cls;
-  std::vector<double> coefK((size_t)K * NC * 4);
+  if (NC >= (1 << 20)) { delete c; return fail(FSCL_ERR_ARG, "more than 2^20 classes"); }
+  if ((size_t)NC * (K + 2) * 32 >= ((size_t)1 << 32)) { delete c; return fail(FSCL_ERR_ARG, "spline table over 4 GiB"); }
+  std::vector<double> coefC((size_t)(K + 2) * NC * 4);
   for (int cl = 0; cl < NC; cl++)
-    for (int k = 0; k < K; k++) {
-      const double *s = p->coef + ((size_t)cl * K + k) * 4;
-      double *d = coefK.data() + ((size_t)k * NC + cl) * 4;
+    for (int k = 0; k < K + 2; k++) {
+      const double *s = p->coef + ((size_t)cl * K + std::min(k, K - 1)) * 4;   // sm-spline.c:53 clamp as rows
+      double *d = coefC.data() + ((size_t)cl * (K + 2) + k) * 4;
       d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3] - p->null_tab[cl];
     }
+  c->n_pad = (c->n + kTile - 1) / kTile * kTile;
+  const int n_tiles = c->n_pad / kTile;
+  std::vector<int> tlo(n_tiles), thi(n_tiles);
+  for (int t = 0; t < n_tiles; t++) {
+    int lo = 0x7FFFFFFF, hi = -0x7FFFFFFF;
+    for (int i = t * kTile; i < std::min(c->n, (t + 1) * kTile); i++) { lo = std::min(lo, c->h_pos[i]); hi = std::max(hi, c->h_pos[i]); }
+    tlo[t] = lo; thi[t] = hi;
+  }
 
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
@@ -349,7 +371,14 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMalloc(&c->d_cls0, sizeof(int) * c->n));
   CK(cudaMalloc(&c->d_chr_start, sizeof(int) * c->n_chr));
   CK(cudaMalloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
-  CK(cudaMalloc(&c->d_coefK, sizeof(double) * coefK.size()));
+  CK(cudaMalloc(&c->d_coefC, sizeof(double) * coefC.size()));
+  CK(cudaMalloc(&c->d_tkey0, sizeof(int) * c->n_pad));
+  CK(cudaMalloc(&c->d_tpos0, sizeof(int) * c->n_pad));
+  CK(cudaMalloc(&c->d_tnull0, sizeof(double) * n_tiles));
+  CK(cudaMalloc(&c->d_tile_lo, sizeof(int) * n_tiles));
+  CK(cudaMalloc(&c->d_tile_hi, sizeof(int) * n_tiles));
+  CK(cudaMemcpy(c->d_tile_lo, tlo.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_tile_hi, thi.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_logT, sizeof(double) * 65536));
   CK(cudaMalloc(&c->d_null, sizeof(double) * NC));
   CK(cudaMalloc(&c->d_terms, sizeof(unsigned long long)));
@@ -358,18 +387,21 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_chr_start, c->chr_start.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_chr_nsnps, c->chr_nsnps.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_coefK, coefK.data(), sizeof(double) * coefK.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_coefC, coefC.data(), sizeof(double) * coefC.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_logT, T.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_null, p->null_tab, sizeof(double) * NC, cudaMemcpyHostToDevice));
   upload_alpha_tables(A);
   CK(cudaGetLastError());
 
   Params &P = c->P;
-  P.n_snps = c->n; P.n_chr = c->n_chr; P.n_cls = NC; P.n_knots = K;
+  P.n_snps = c->n; P.n_pad = c->n_pad; P.n_chr = c->n_chr; P.n_cls = NC; P.n_knots = K;
   P.eval_range = p->eval_range; P.bp_resl = p->bp_resl;
-  P.inv_step = 1.0 / p->step; P.off = 20.0 / p->step;
+  P.inv_step = 1.0 / p->step; P.off_magic = 20.0 / p->step - 0.5 + 6755399441055744.0;
   P.pos = c->d_pos; P.chr_start = c->d_chr_start; P.chr_nsnps = c->d_chr_nsnps;
-  P.coefK = c->d_coefK; P.logT = c->d_logT; P.null_tab = c->d_null;
+  P.coefC = c->d_coefC; P.row_doubles = (K + 2) * 4; P.tile_lo = c->d_tile_lo; P.tile_hi = c->d_tile_hi; P.logT = c->d_logT; P.null_tab = c->d_null;
+  launch_bucket(c->n, c->n_pad, c->d_cls0, 0, c->d_pos, c->d_null, c->d_tkey0, c->d_tpos0, c->d_tnull0, 1, c->stream);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
   *ctx_out = c;
   return FSCL_OK;
 }
@@ -379,7 +411,8 @@ extern "C" void fscl_destroy(void *ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_pos); cudaFree(c->d_cls0); cudaFree(c->d_chr_start); cudaFree(c->d_chr_nsnps);
-  cudaFree(c->d_coefK); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
+  cudaFree(c->d_coefC); cudaFree(c->d_tkey0); cudaFree(c->d_tpos0); cudaFree(c->d_tnull0); cudaFree(c->d_tnull);
+  cudaFree(c->d_tile_lo); cudaFree(c->d_tile_hi); cudaFree(c->d_tkey); cudaFree(c->d_tpos); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
   cudaFree(c->d_pcls); cudaFree(c->d_scratch); cudaFree(c->d_blocks); cudaFree(c->d_blkoff);
   cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_matrix);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -412,7 +445,7 @@ static int eval_list(Ctx *c, int n, const int32_t *chr, const int32_t *start, co
     if (chr[i] < 0 || chr[i] >= c->n_chr) return fail(FSCL_ERR_ARG, "chromosome index out of range");
     c->h_tasks[i] = Task{0, chr[i], start[i], end ? end[i] : start[i], 0};
   }
-  int rc = run_tasks(c, c->d_cls0, flags | kFlagNullSum);
+  int rc = run_tasks(c, false, flags | kFlagNullSum);
   if (rc) return rc;
   for (int i = 0; i < n; i++) to_pt(c->h_out[i], out[i]);
   c->stats.n_grid_evals += n;
@@ -437,7 +470,7 @@ extern "C" int fscl_scan_chromosome(void *ctx, int G, fscl_pt_t *out, int cap, i
   int n = enum_cells(c, G, &c->h_tasks);
   *n_out = n;
   if (n > cap) return fail(FSCL_ERR_ARG, "output capacity too small");
-  int rc = run_tasks(c, c->d_cls0, kFlagNullSum);
+  int rc = run_tasks(c, false, kFlagNullSum);
   if (rc) return rc;
   std::vector<fscl_pt_t> pts(n);
   for (int i = 0; i < n; i++) to_pt(c->h_out[i], pts[i]);
@@ -467,6 +500,9 @@ static int upload_blocks(Ctx *c, const std::vector<int4> &blocks, const std::vec
 static int apply_blocks(Ctx *c, int n_slots) {
   CK(cudaEventRecord(c->ev0, c->stream));
   launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, n_slots, c->stream);
+  CK(cudaGetLastError());
+  launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull,
+                n_slots, c->stream);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -609,7 +645,7 @@ static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, i
         int start = p.sweep_pos - (p.sweep_pos % G);                    // D4
         c->h_tasks[(size_t)q * na + a] = Task{q, p.chr, start, start + G, (int)((size_t)S.my_rows[q] * na + a)};
       }
-    rc = run_tasks(c, c->d_pcls, 0, false, dm); if (rc) return rc;
+    rc = run_tasks(c, true, 0, false, dm); if (rc) return rc;
     c->stats.n_grid_evals += (int64_t)ns * (int64_t)na;
   } else {
     CK(cudaStreamSynchronize(c->stream));
@@ -722,7 +758,6 @@ extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_ter
   CK(cudaSetDevice(c->device));
   std::vector<Task> cells;
   enum_cells(c, G, &cells);
-  const int *d_cls = c->d_cls0;
   int ns = 1;
   if (n_perm_slots > 0) {
     ns = n_perm_slots;
@@ -735,7 +770,6 @@ extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_ter
     rc = upload_blocks(c, blocks, off); if (rc) return rc;
     rc = apply_blocks(c, ns); if (rc) return rc;
     c->stats.n_blocks += (int64_t)blocks.size();
-    d_cls = c->d_pcls;
   }
   c->h_tasks.resize((size_t)ns * cells.size());
   for (int q = 0; q < ns; q++)
@@ -745,7 +779,7 @@ extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_ter
       c->h_tasks[(size_t)q * cells.size() + a] = t;
     }
   if (count_terms) CK(cudaMemsetAsync(c->d_terms, 0, sizeof(unsigned long long), c->stream));
-  int rc = run_tasks(c, d_cls, count_terms ? kFlagCount : 0, false);
+  int rc = run_tasks(c, n_perm_slots > 0, count_terms ? kFlagCount : 0, false);
   if (rc) return rc;
   if (count_terms && terms_out) {
     unsigned long long v = 0;

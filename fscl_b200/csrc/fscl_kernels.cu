@@ -54,10 +54,20 @@ __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
   R.dnear = d < 0 ? -d : d;
 }
 
+// 32-byte coefficient row in one 256-bit load (LDG.E.256)
+__device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, double &c2, double &c3) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(p));
+}
+
 // One pass over the window for the alpha list in c_alpha row `row`:
 // S[j] = sum over window sites with d <= dmax[j] of spline_cls(logt(d)+la[j]) - null
 // (sm_likelihood sm-search.c:105-150; the walks' "break at first exceed" equals
 // the distance cut because logt is monotone; nearest failing => empty sum).
+//
+// Sites are read from the class-bucketed tiles (bucket_kernel): inside a tile of
+// kTile consecutive sites the records are sorted by class, so the 32 lanes of a
+// warp mostly share one spline and neighbouring knots and the 32-byte
+// coefficient rows of a warp collapse to one or two L1 wavefronts.
 //
 // The reference accumulates the terms onto null_logl (about -1e5..-1e6), so sums
 // below ulp(null_logl)/2 vanish and candidates tie EXACTLY (first one wins,
@@ -65,8 +75,9 @@ __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
 // returning S[j] = (N + sum_j) - N with N the window null sum, which the coarse
 // pass (WITHN) accumulates alongside.
 template <int NA, bool COUNT, bool WITHN>
-__device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ cls, PtS &R,
-                                          int row, double (*red)[kMaxFine + 1], double *S,
+__device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ tkey,
+                                          const int *__restrict__ tpos, const double *__restrict__ tnull,
+                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
                                           unsigned long long &nterms) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na_all = c_alpha.n[row];
@@ -80,34 +91,89 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
   for (int j = 0; j < NA; j++) acc[j] = 0.0;
   if (na > 0 || WITHN) {
     const int sweep = R.sweep_pos, ws = R.wstart, we = R.wend;
-    const int *__restrict__ gpos = P.pos;
-    const double2 *__restrict__ coef = reinterpret_cast<const double2 *>(P.coefK);
-    const int ncls = P.n_cls, kmax = P.n_knots - 1;
-    const double inv_step = P.inv_step, off = P.off;
-    for (int base = (ws & ~31) + warp * 32; base <= we; base += kScanWarps * 32) {
-      const int i = base + lane;
-      const bool valid = (i >= ws) && (i <= we);
-      int d = 0x7FFFFFFF, c = 0;
-      if (valid) {
-        d = __ldg(gpos + i) - sweep;
-        d = d < 0 ? -d : d;
-        c = __ldg(cls + i);
-      }
-      const double x0 = valid ? dev_logt(P.logT, d) : 0.0;
-      if (WITHN && valid) accn += __ldg(P.null_tab + c);
+    const unsigned wlen = (unsigned)(we - ws);
+    const char *__restrict__ coef = reinterpret_cast<const char *>(P.coefC);
+    const unsigned rowbytes = (unsigned)P.row_doubles * 8u;
+    const unsigned kclamp = (unsigned)P.n_knots + 1u;
+    const double inv_step = P.inv_step, offm = P.off_magic;
+    const int t0 = ws / kTile, t1 = we / kTile;
+    for (int t = t0; t <= t1; t++) {
+      // per-tile alpha classification from the tile's position bounds (warp-uniform)
+      const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+      const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
+      const int dfar = max(dlo, dhi);
+      const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
+      const bool inside = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
+      int jany = 0, jfull = 0;
 #pragma unroll
       for (int j = 0; j < NA; j++) {
-        if (j >= na) break;
-        const bool inc = valid && d <= c_alpha.dmax[row][j];
-        if (!__any_sync(0xFFFFFFFFu, inc)) break;
-        const double x = x0 + c_alpha.la[row][j];
-        int k = __double2int_rz(fma(x, inv_step, off));
-        k = min(max(k, 0), kmax);
-        const double2 *r = coef + ((size_t)k * ncls + c) * 2;
-        const double2 a = __ldg(r), b = __ldg(r + 1);
-        const double y = fma(x, fma(x, fma(x, a.x, a.y), b.x), b.y);
-        if (inc) acc[j] += y;
-        if (COUNT) nterms += inc ? 1ull : 0ull;
+        if (j < na && c_alpha.dmax[row][j] >= dnr) jany = j + 1;
+        if (j < na && c_alpha.dmax[row][j] >= dfar) jfull = j + 1;
+      }
+      if (!inside) jfull = 0;
+      if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
+      if (jany == 0 && !(WITHN && !inside)) continue;
+      for (int ch = warp; ch < kTile / 32; ch += kScanWarps) {
+        const int i = t * kTile + ch * 32 + lane;
+        const int key = __ldg(tkey + i);
+        int d = __ldg(tpos + i) - sweep;
+        d = d < 0 ? -d : d;
+        const unsigned c = (unsigned)key & 0xFFFFFu;
+        const double x0 = dev_logt(P.logT, d);
+        const char *crow = coef + (size_t)c * rowbytes;
+        asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
+        if (!inside) {
+          const int orig = t * kTile + (int)((unsigned)key >> 20);
+          const bool valid = (unsigned)(orig - ws) <= wlen;
+          if (!valid) d = 0x7FFFFFFF;             // dmax tables are capped below INT_MAX
+          if (WITHN && valid) accn += __ldg(P.null_tab + c);
+        }
+        // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
+        // Groups of four issue their coefficient loads back to back before the FMAs.
+#pragma unroll
+        for (int g = 0; g < NA; g += 4) {
+          if (g >= jfull) break;
+          if (g + 4 <= NA && g + 4 <= jfull) {
+            double x[4], c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              x[u] = x0 + c_alpha.la[row][g + u];
+              // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
+              // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
+              const unsigned k = (unsigned)__double2loint(fma(x[u], inv_step, offm));
+              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[u], c1[u], c2[u], c3[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[g + u] += fma(x[u], fma(x[u], fma(x[u], c0[u], c1[u]), c2[u]), c3[u]);
+            if (COUNT) nterms += 4ull;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (g + u >= NA || g + u >= jfull) break;
+              const double x = x0 + c_alpha.la[row][g + u];
+              const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
+              double c0, c1, c2, c3;
+              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+              acc[g + u] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
+              if (COUNT) nterms += 1ull;
+            }
+          }
+        }
+        // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+#pragma unroll
+        for (int j = 0; j < NA; j++) {
+          if (j < jfull) continue;
+          if (j >= jany) break;
+          const bool inc = d <= c_alpha.dmax[row][j];
+          const double x = x0 + c_alpha.la[row][j];
+          unsigned k = (unsigned)max(__double2loint(fma(x, inv_step, offm)), 0);
+          k = min(k, kclamp);
+          double c0, c1, c2, c3;
+          ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+          const double y = fma(x, fma(x, fma(x, c0, c1), c2), c3);
+          if (inc) acc[j] += y;
+          if (COUNT) nterms += inc ? 1ull : 0ull;
+        }
       }
     }
   }
@@ -144,11 +210,12 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 
 // search_maxalpha sm-search.c:269-300 at one position
 template <bool COUNT>
-__device__ void dev_eval(const Params &P, const int *__restrict__ cls, int chr, int pos, PtS &R,
+__device__ void dev_eval(const Params &P, const int *__restrict__ tkey, const int *__restrict__ tpos,
+                         const double *__restrict__ tnull, int chr, int pos, PtS &R,
                          double (*red)[kMaxFine + 1], double *S, int *s_row, unsigned long long &nterms) {
   if (threadIdx.x == 0) dev_init_point(P, chr, pos, R);
   __syncthreads();
-  dev_phase<kCoarse, COUNT, true>(P, cls, R, kCoarse, red, S, nterms);
+  dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, R, kCoarse, red, S, nterms);
   if (threadIdx.x == 0) {
     // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
     // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
@@ -160,7 +227,7 @@ __device__ void dev_eval(const Params &P, const int *__restrict__ cls, int chr, 
   }
   __syncthreads();
   const int row = *s_row;
-  dev_phase<kMaxFine, COUNT, false>(P, cls, R, row, red, S, nterms);
+  dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, R, row, red, S, nterms);
   if (threadIdx.x == 0) {
     double bs = R.clr, la = R.lalpha;
     const int nf = c_alpha.n[row];
@@ -172,26 +239,29 @@ __device__ void dev_eval(const Params &P, const int *__restrict__ cls, int chr, 
 
 // search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell)
 template <bool COUNT>
-__global__ void __launch_bounds__(kScanThreads, 4)
+__global__ void __launch_bounds__(kScanThreads, kScanMinBlocks)
 scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tasks, OutPt *__restrict__ out,
-                  const int *__restrict__ cls_all, int flags, unsigned long long *term_counter,
+                  const int *__restrict__ tkey_all, const int *__restrict__ tpos_all,
+                  const double *__restrict__ tnull_all, int flags, unsigned long long *term_counter,
                   double *__restrict__ clr_matrix) {
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
   __shared__ int s_row, s_go;
   const Task t = tasks[blockIdx.x];
-  const int *__restrict__ cls = cls_all + (size_t)t.slot * P.n_snps;
+  const int *__restrict__ tkey = tkey_all + (size_t)t.slot * P.n_pad;
+  const int *__restrict__ tpos = tpos_all + (size_t)t.slot * P.n_pad;
+  const double *__restrict__ tnull = tnull_all + (size_t)t.slot * (P.n_pad / kTile);
   unsigned long long nterms = 0;
 
-  dev_eval<COUNT>(P, cls, t.chr, t.start_pos, A, red, S, &s_row, nterms);
+  dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, t.start_pos, A, red, S, &s_row, nterms);
   if (!(flags & kFlagSingle)) {
-    dev_eval<COUNT>(P, cls, t.chr, t.end_pos, B, red, S, &s_row, nterms);
+    dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, t.end_pos, B, red, S, &s_row, nterms);
     for (;;) {
       if (threadIdx.x == 0) s_go = (B.sweep_pos - A.sweep_pos > P.bp_resl);
       __syncthreads();
       if (!s_go) break;
-      dev_eval<COUNT>(P, cls, t.chr, (A.sweep_pos + B.sweep_pos) / 2, M, red, S, &s_row, nterms);
+      dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, (A.sweep_pos + B.sweep_pos) / 2, M, red, S, &s_row, nterms);
       if (threadIdx.x == 0) {
         if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M; else A = M;   // scan-chromosome.c:116
       }
@@ -215,13 +285,13 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   }
 }
 
-void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *cls_all, int n_tasks,
-                 int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *tkey_all, const int *tpos_all,
+                 const double *tnull_all, int n_tasks, int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
   if (n_tasks <= 0) return;
   if (flags & kFlagCount)
-    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, cls_all, flags, term_counter, clr_matrix);
+    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, tkey_all, tpos_all, tnull_all, flags, term_counter, clr_matrix);
   else
-    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, cls_all, flags, term_counter, clr_matrix);
+    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, tkey_all, tpos_all, tnull_all, flags, term_counter, clr_matrix);
 }
 
 // ---------------------------------------------------------------------------
@@ -258,6 +328,64 @@ permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, 
     }
     __syncthreads();
   }
+}
+
+// ---------------------------------------------------------------------------
+// Class-bucketing of one genome instance: every tile of kTile consecutive sites
+// is sorted by (class, index) with a shared-memory bitonic network; the record
+// is key = class | index_in_tile << 20 plus the site's position.
+__global__ void __launch_bounds__(kTile / 2)
+bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stride,
+              const int *__restrict__ pos, const double *__restrict__ null_tab, int *__restrict__ tkey_all,
+              int *__restrict__ tpos_all, double *__restrict__ tnull_all) {
+  __shared__ unsigned keys[kTile];
+  __shared__ double wsum[kTile / 64];
+  const int tile = blockIdx.x, slot = blockIdx.y;
+  const int *cls = cls_all + (size_t)slot * cls_stride;
+  const int base = tile * kTile;
+  for (int e = threadIdx.x; e < kTile; e += kTile / 2) {
+    const int gi = base + e;
+    keys[e] = ((gi < n ? (unsigned)cls[gi] : 0u) << 12) | (unsigned)e;
+  }
+  __syncthreads();
+  for (int k = 2; k <= kTile; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int t = threadIdx.x;
+      const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+      const bool up = (lo & k) == 0;
+      const unsigned a = keys[lo], b = keys[hi];
+      if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      __syncthreads();
+    }
+  int *tkey = tkey_all + (size_t)slot * n_pad, *tpos = tpos_all + (size_t)slot * n_pad;
+  for (int e = threadIdx.x; e < kTile; e += kTile / 2) {
+    const unsigned kk = keys[e];
+    const int lidx = (int)(kk & 0xFFFu), gi = base + lidx;
+    tkey[base + e] = (int)((kk >> 12) | ((unsigned)lidx << 20));
+    tpos[base + e] = gi < n ? __ldg(pos + gi) : 0;
+  }
+  // null log-likelihood of the tile (fixed tree; only complete tiles are ever read)
+  double v = 0.0;
+  for (int e = threadIdx.x; e < kTile; e += kTile / 2)
+    if (base + e < n) v += __ldg(null_tab + cls[base + e]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tsum = 0.0;
+    for (int w = 0; w < kTile / 64; w++) tsum += wsum[w];
+    tnull_all[(size_t)slot * (n_pad / kTile) + tile] = tsum;
+  }
+}
+
+void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
+                   const double *null_tab, int *tkey_all, int *tpos_all, double *tnull_all, int n_slots,
+                   cudaStream_t s) {
+  if (n_slots <= 0) return;
+  dim3 grid(n_pad / kTile, n_slots);
+  bucket_kernel<<<grid, kTile / 2, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, tkey_all, tpos_all,
+                                          tnull_all);
 }
 
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,

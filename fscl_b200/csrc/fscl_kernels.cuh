@@ -22,15 +22,20 @@ constexpr int kCoarse = 11;      // coarse alpha candidates (sm-search.c:276-282
 constexpr int kMaxFine = 15;     // fine alpha candidates   (sm-search.c:284-296)
 constexpr int kRows = kCoarse + 1;  // fine lists for each coarse argmax + the coarse list (row 11)
 constexpr int kScanThreads = 256;
+constexpr int kScanMinBlocks = 3;   // 85 registers: the 15 fine-alpha accumulators do not spill
+constexpr int kTile = 2048;         // sites per class-bucketed tile (<= 4096: 12-bit index in the key)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kPermThreads = 1024;
 
 struct Params {
-  int n_snps, n_chr, n_cls, n_knots, eval_range, bp_resl;
-  double inv_step, off;            // knot = trunc(x * inv_step + off), off = 20 / step
+  int n_snps, n_pad, n_chr, n_cls, n_knots, eval_range, bp_resl;
+  double inv_step, off_magic;      // knot = low word of x*inv_step + (20/step - 0.5 + 2^52 + 2^51)
   const int *pos;                  // [n_snps]
   const int *chr_start, *chr_nsnps;
-  const double *coefK;             // [n_knots][n_cls][4], c3 already minus null_tab[cls]
+  const double *coefC;             // [n_cls][n_knots+2][4], c3 already minus null_tab[cls]; the two
+                                   // extra rows repeat the last knot so x == 4 needs no clamp
+  int row_doubles;                 // (n_knots + 2) * 4
+  const int *tile_lo, *tile_hi;    // [n_pad / kTile] smallest / largest position inside each tile
   const double *logT;              // [65536]
   const double *null_tab;          // [n_cls]
 };
@@ -52,8 +57,11 @@ struct AlphaTables {
 
 void upload_alpha_tables(const AlphaTables &t);
 
-void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *cls_all, int n_tasks,
-                 int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *tkey_all, const int *tpos_all,
+                 const double *tnull_all, int n_tasks, int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
+void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
+                   const double *null_tab, int *tkey_all, int *tpos_all, double *tnull_all, int n_slots,
+                   cudaStream_t s);
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
                     const int *blk_off, int n_slots, cudaStream_t s);
 void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);

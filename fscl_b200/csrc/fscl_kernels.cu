@@ -97,69 +97,101 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const unsigned kclamp = (unsigned)P.n_knots + 1u;
     const double inv_step = P.inv_step, offm = P.off_magic;
     const int t0 = ws / kTile, t1 = we / kTile;
-    for (int t = t0; t <= t1; t++) {
-      // per-tile alpha classification from the tile's position bounds (warp-uniform)
-      const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
-      const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
-      const int dfar = max(dlo, dhi);
-      const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
-      const bool inside = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
-      int jany = 0, jfull = 0;
-#pragma unroll
-      for (int j = 0; j < NA; j++) {
-        if (j < na && c_alpha.dmax[row][j] >= dnr) jany = j + 1;
-        if (j < na && c_alpha.dmax[row][j] >= dfar) jfull = j + 1;
-      }
-      if (!inside) jfull = 0;
-      if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
-      if (jany == 0 && !(WITHN && !inside)) continue;
-      for (int ch = warp; ch < kTile / 32; ch += kScanWarps) {
-        const int i = t * kTile + ch * 32 + lane;
-        const int key = __ldg(tkey + i);
-        int d = __ldg(tpos + i) - sweep;
-        d = d < 0 ? -d : d;
-        const unsigned c = (unsigned)key & 0xFFFFFu;
-        const double x0 = dev_logt(P.logT, d);
-        const char *crow = coef + (size_t)c * rowbytes;
-        asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
-        if (!inside) {
-          const int orig = t * kTile + (int)((unsigned)key >> 20);
-          const bool valid = (unsigned)(orig - ws) <= wlen;
-          if (!valid) d = 0x7FFFFFFF;             // dmax tables are capped below INT_MAX
-          if (WITHN && valid) accn += __ldg(P.null_tab + c);
+    // tiles that can hold an admitted site: [ta, tb] (every tile when the null sum is wanted)
+    int ta = t0, tb = t1;
+    if (!WITHN) {
+      const int cut = c_alpha.dmax[row][0];          // widest cut of the list
+      ta = 0x7FFFFFFF; tb = -1;
+      for (int b0 = t0; b0 <= t1; b0 += 32) {
+        const int t = b0 + lane;
+        bool hit = false;
+        if (t <= t1) {
+          const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+          const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
+          hit = dnr <= cut;
         }
-        // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
-        // Groups of four issue their coefficient loads back to back before the FMAs.
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (m) { ta = min(ta, b0 + __ffs(m) - 1); tb = max(tb, b0 + 31 - __clz(m)); }
+      }
+    }
+    constexpr int CH = kTile / 32 / kScanWarps;       // chunks of a tile per warp
+    const int n_total = tb >= ta ? (tb - ta + 1) * CH : 0;
+    auto rec_index = [&](int n) { return (ta + n / CH) * kTile + ((n % CH) * kScanWarps + warp) * 32 + lane; };
+    // software pipeline: records are fetched two chunks ahead, the log-distance one chunk ahead,
+    // so both L2 round trips overlap the FMAs of the current chunk
+    int key1 = 0, pos1 = 0, key2 = 0, pos2 = 0, d1 = 0;
+    double x1 = 0.0;
+    if (n_total > 0) { const int i = rec_index(0); key1 = __ldg(tkey + i); pos1 = __ldg(tpos + i); }
+    if (n_total > 1) { const int i = rec_index(1); key2 = __ldg(tkey + i); pos2 = __ldg(tpos + i); }
+    if (n_total > 0) { d1 = pos1 - sweep; d1 = d1 < 0 ? -d1 : d1; x1 = dev_logt(P.logT, d1); }
+    int jany = 0, jfull = 0;
+    bool inside = false;
+    for (int n = 0; n < n_total; n++) {
+      const int key = key1;
+      int d = d1;
+      const double x0 = x1;
+      key1 = key2; pos1 = pos2;
+      if (n + 2 < n_total) { const int i = rec_index(n + 2); key2 = __ldg(tkey + i); pos2 = __ldg(tpos + i); }
+      if (n + 1 < n_total) { d1 = pos1 - sweep; d1 = d1 < 0 ? -d1 : d1; x1 = dev_logt(P.logT, d1); }
+      const int t = ta + n / CH;
+      if (n % CH == 0) {
+        // per-tile alpha classification from the tile's position bounds (warp-uniform)
+        const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+        const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
+        const int dfar = max(dlo, dhi);
+        const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
+        inside = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
+        jany = 0; jfull = 0;
 #pragma unroll
-        for (int g = 0; g < NA; g += 4) {
-          if (g >= jfull) break;
-          if (g + 4 <= NA && g + 4 <= jfull) {
-            double x[4], c0[4], c1[4], c2[4], c3[4];
+        for (int j = 0; j < NA; j++) {
+          if (j < na && c_alpha.dmax[row][j] >= dnr) jany = j + 1;
+          if (j < na && c_alpha.dmax[row][j] >= dfar) jfull = j + 1;
+        }
+        if (!inside) jfull = 0;
+        if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
+      }
+      const unsigned c = (unsigned)key & 0xFFFFFu;
+      const char *crow = coef + (size_t)c * rowbytes;
+      asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
+      if (!inside) {
+        const int orig = t * kTile + (int)((unsigned)key >> 20);
+        const bool valid = (unsigned)(orig - ws) <= wlen;
+        if (!valid) d = 0x7FFFFFFF;             // dmax tables are capped below INT_MAX
+        if (WITHN && valid) accn += __ldg(P.null_tab + c);
+      }
+      // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
+      // Groups of four issue their coefficient loads back to back before the FMAs.
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              x[u] = x0 + c_alpha.la[row][g + u];
-              // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
-              // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
-              const unsigned k = (unsigned)__double2loint(fma(x[u], inv_step, offm));
-              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[u], c1[u], c2[u], c3[u]);
-            }
+      for (int g = 0; g < NA; g += 4) {
+        if (g >= jfull) break;
+        if (g + 4 <= NA && g + 4 <= jfull) {
+          double x[4], c0[4], c1[4], c2[4], c3[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) acc[g + u] += fma(x[u], fma(x[u], fma(x[u], c0[u], c1[u]), c2[u]), c3[u]);
-            if (COUNT) nterms += 4ull;
-          } else {
+          for (int u = 0; u < 4; u++) {
+            x[u] = x0 + c_alpha.la[row][g + u];
+            // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
+            // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
+            const unsigned k = (unsigned)__double2loint(fma(x[u], inv_step, offm));
+            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[u], c1[u], c2[u], c3[u]);
+          }
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-              if (g + u >= NA || g + u >= jfull) break;
-              const double x = x0 + c_alpha.la[row][g + u];
-              const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
-              double c0, c1, c2, c3;
-              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
-              acc[g + u] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
-              if (COUNT) nterms += 1ull;
-            }
+          for (int u = 0; u < 4; u++) acc[g + u] += fma(x[u], fma(x[u], fma(x[u], c0[u], c1[u]), c2[u]), c3[u]);
+          if (COUNT) nterms += 4ull;
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            if (g + u >= NA || g + u >= jfull) break;
+            const double x = x0 + c_alpha.la[row][g + u];
+            const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
+            double c0, c1, c2, c3;
+            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+            acc[g + u] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
+            if (COUNT) nterms += 1ull;
           }
         }
-        // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+      }
+      // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+      if (jany > jfull) {
 #pragma unroll
         for (int j = 0; j < NA; j++) {
           if (j < jfull) continue;

@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfscl_b200.so")
+LIB_PATH = os.environ.get("FSCL_B200_LIB", os.path.join(HERE, "libfscl_b200.so"))
 NULL_SAVE = 10000
 
 RNG_GLIBC, RNG_PHILOX, RNG_LIBC = 0, 1, 2

@@ -318,6 +318,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   if (p->device < 0 || p->device >= ndev) return fail(FSCL_ERR_ARG, "bad device ordinal");
   if (p->n_snps <= 0 || p->n_chr <= 0 || p->n_cls <= 0 || p->n_knots <= 0)
     return fail(FSCL_ERR_ARG, "empty problem");
+  if (p->eval_range < 1 || p->eval_range > 81920)
+    return fail(FSCL_ERR_ARG, "eval_range must be in [1, 81920] (fscl.c:175)");
   CK(cudaSetDevice(p->device));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, p->device));

@@ -54,9 +54,38 @@ __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
   R.dnear = d < 0 ? -d : d;
 }
 
+// record streams are read once per pass: keep them out of L1 so that the spline rows and the
+// log table stay resident there
+__device__ __forceinline__ int ld_stream(const int *p) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+// mid-range log-table entries (d >> 8) are touched about once per tile pass
+__device__ __forceinline__ double ld_lut_mid(const double *p) {
+#ifdef FSCL_LUT_NOALLOC
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
+
 // 32-byte coefficient row in one 256-bit load (LDG.E.256)
 __device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, double &c2, double &c3) {
+#if !defined(FSCL_EXP)
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(p));
+#elif FSCL_EXP == 1     /* timing experiments only */
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y;
+#elif FSCL_EXP == 2
+  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+  c0 = a.x; c1 = a.y; c2 = 0.25; c3 = 0.125;
+#elif FSCL_EXP == 3
+  c0 = 1e-3; c1 = 2e-3; c2 = 0.25 + (double)(reinterpret_cast<size_t>(p) & 0xFF); c3 = 0.125;
+#endif
 }
 
 // One pass over the window for the alpha list in c_alpha row `row`:
@@ -67,7 +96,7 @@ __device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, 
 // Sites are read from the class-bucketed tiles (bucket_kernel): inside a tile of
 // kTile consecutive sites the records are sorted by class, so the 32 lanes of a
 // warp mostly share one spline and neighbouring knots and the 32-byte
-// coefficient rows of a warp collapse to one or two L1 wavefronts.
+// coefficient rows of a warp come from one or two L1 lines.
 //
 // The reference accumulates the terms onto null_logl (about -1e5..-1e6), so sums
 // below ulp(null_logl)/2 vanish and candidates tie EXACTLY (first one wins,
@@ -93,6 +122,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const int sweep = R.sweep_pos, ws = R.wstart, we = R.wend;
     const unsigned wlen = (unsigned)(we - ws);
     const char *__restrict__ coef = reinterpret_cast<const char *>(P.coefC);
+    const double *__restrict__ T = P.logT;
     const unsigned rowbytes = (unsigned)P.row_doubles * 8u;
     const unsigned kclamp = (unsigned)P.n_knots + 1u;
     const double inv_step = P.inv_step, offm = P.off_magic;
@@ -114,27 +144,27 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         if (m) { ta = min(ta, b0 + __ffs(m) - 1); tb = max(tb, b0 + 31 - __clz(m)); }
       }
     }
+    // A warp owns chunks {warp, warp+8, ...} of every tile and walks them in batches of kB:
+    // the kB records of the NEXT batch are fetched while the current one is evaluated,
+    // the kB log-distances and the coefficient rows of four alphas are each issued together.
     constexpr int CH = kTile / 32 / kScanWarps;       // chunks of a tile per warp
-    const int n_total = tb >= ta ? (tb - ta + 1) * CH : 0;
-    auto rec_index = [&](int n) { return (ta + n / CH) * kTile + ((n % CH) * kScanWarps + warp) * 32 + lane; };
-    // software pipeline: records are fetched two chunks ahead, the log-distance one chunk ahead,
-    // so both L2 round trips overlap the FMAs of the current chunk
-    int key1 = 0, pos1 = 0, key2 = 0, pos2 = 0, d1 = 0;
-    double x1 = 0.0;
-    if (n_total > 0) { const int i = rec_index(0); key1 = __ldg(tkey + i); pos1 = __ldg(tpos + i); }
-    if (n_total > 1) { const int i = rec_index(1); key2 = __ldg(tkey + i); pos2 = __ldg(tpos + i); }
-    if (n_total > 0) { d1 = pos1 - sweep; d1 = d1 < 0 ? -d1 : d1; x1 = dev_logt(P.logT, d1); }
-    int jany = 0, jfull = 0;
+    constexpr int kB = FSCL_KB < CH ? FSCL_KB : CH;
+    constexpr int HB = CH / kB;                       // batches per tile
+    static_assert(CH % kB == 0, "tile must split into whole batches");
+    const int n_batches = tb >= ta ? (tb - ta + 1) * HB : 0;
+    const int woff = warp * 32 + lane;
+    auto batch_base = [&](int h) { return (ta + h / HB) * kTile + (h % HB) * (kB * kScanWarps * 32) + woff; };
+    int nkey[kB], npos[kB];
+    if (n_batches > 0) {
+      const int i = batch_base(0);
+#pragma unroll
+      for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
+    }
+    int jany = 0, jfull = 0, lut = 0;
     bool inside = false;
-    for (int n = 0; n < n_total; n++) {
-      const int key = key1;
-      int d = d1;
-      const double x0 = x1;
-      key1 = key2; pos1 = pos2;
-      if (n + 2 < n_total) { const int i = rec_index(n + 2); key2 = __ldg(tkey + i); pos2 = __ldg(tpos + i); }
-      if (n + 1 < n_total) { d1 = pos1 - sweep; d1 = d1 < 0 ? -d1 : d1; x1 = dev_logt(P.logT, d1); }
-      const int t = ta + n / CH;
-      if (n % CH == 0) {
+    for (int h = 0; h < n_batches; h++) {
+      const int t = ta + h / HB;
+      if (h % HB == 0) {
         // per-tile alpha classification from the tile's position bounds (warp-uniform)
         const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
         const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
@@ -148,63 +178,93 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           if (j < na && c_alpha.dmax[row][j] >= dfar) jfull = j + 1;
         }
         if (!inside) jfull = 0;
+        // which branch of logt (sm-search.c:40-46) the whole tile takes: 2 = >>16, 1 = >>8, 0 = mixed
+        lut = (inside && dnr > 0xFFFFFF) ? 2 : ((inside && dnr > 0xFFFF && dfar <= 0xFFFFFF) ? 1 : 0);
         if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
       }
-      const unsigned c = (unsigned)key & 0xFFFFFu;
-      const char *crow = coef + (size_t)c * rowbytes;
-      asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
-      if (!inside) {
-        const int orig = t * kTile + (int)((unsigned)key >> 20);
-        const bool valid = (unsigned)(orig - ws) <= wlen;
-        if (!valid) d = 0x7FFFFFFF;             // dmax tables are capped below INT_MAX
-        if (WITHN && valid) accn += __ldg(P.null_tab + c);
+      int key[kB], d[kB];
+      double x0[kB];
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        key[u] = nkey[u];
+        const int dd = npos[u] - sweep;
+        d[u] = dd < 0 ? -dd : dd;
       }
-      // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
-      // Groups of four issue their coefficient loads back to back before the FMAs.
+      if (lut == 2) {
 #pragma unroll
-      for (int g = 0; g < NA; g += 4) {
-        if (g >= jfull) break;
-        if (g + 4 <= NA && g + 4 <= jfull) {
-          double x[4], c0[4], c1[4], c2[4], c3[4];
+        for (int u = 0; u < kB; u++) x0[u] = 11.783502069519070 + __ldg(T + (d[u] >> 16));
+      } else if (lut == 1) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            x[u] = x0 + c_alpha.la[row][g + u];
-            // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
-            // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
-            const unsigned k = (unsigned)__double2loint(fma(x[u], inv_step, offm));
-            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[u], c1[u], c2[u], c3[u]);
-          }
+        for (int u = 0; u < kB; u++) x0[u] = 5.545177444479562 + ld_lut_mid(T + (d[u] >> 8));
+      } else {
 #pragma unroll
-          for (int u = 0; u < 4; u++) acc[g + u] += fma(x[u], fma(x[u], fma(x[u], c0[u], c1[u]), c2[u]), c3[u]);
-          if (COUNT) nterms += 4ull;
-        } else {
+        for (int u = 0; u < kB; u++) x0[u] = dev_logt(T, d[u]);
+      }
+      if (h + 1 < n_batches) {
+        const int i = batch_base(h + 1);
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            if (g + u >= NA || g + u >= jfull) break;
-            const double x = x0 + c_alpha.la[row][g + u];
-            const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
-            double c0, c1, c2, c3;
-            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
-            acc[g + u] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
-            if (COUNT) nterms += 1ull;
+        for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
+      }
+#pragma unroll
+      for (int u = 0; u < kB; u++) {
+        const unsigned c = (unsigned)key[u] & 0xFFFFFu;
+        const char *crow = coef + (size_t)c * rowbytes;
+        asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
+        int dq = d[u];
+        const double xq = x0[u];
+        if (!inside) {
+          const int orig = t * kTile + (int)((unsigned)key[u] >> 20);
+          const bool valid = (unsigned)(orig - ws) <= wlen;
+          if (!valid) dq = 0x7FFFFFFF;            // dmax tables are capped below INT_MAX
+          if (WITHN && valid) accn += __ldg(P.null_tab + c);
+        }
+        // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
+        // Groups of four issue their coefficient loads back to back before the FMAs.
+#pragma unroll
+        for (int g = 0; g < NA; g += 4) {
+          if (g >= jfull) break;
+          if (g + 4 <= NA && g + 4 <= jfull) {
+            double x[4], c0[4], c1[4], c2[4], c3[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              x[v] = xq + c_alpha.la[row][g + v];
+              // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
+              // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
+              const unsigned k = (unsigned)__double2loint(fma(x[v], inv_step, offm));
+              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[v], c1[v], c2[v], c3[v]);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++) acc[g + v] += fma(x[v], fma(x[v], fma(x[v], c0[v], c1[v]), c2[v]), c3[v]);
+            if (COUNT) nterms += 4ull;
+          } else {
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+              if (g + v >= NA || g + v >= jfull) break;
+              const double x = xq + c_alpha.la[row][g + v];
+              const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
+              double c0, c1, c2, c3;
+              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+              acc[g + v] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
+              if (COUNT) nterms += 1ull;
+            }
           }
         }
-      }
-      // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
-      if (jany > jfull) {
+        // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+        if (jany > jfull) {
 #pragma unroll
-        for (int j = 0; j < NA; j++) {
-          if (j < jfull) continue;
-          if (j >= jany) break;
-          const bool inc = d <= c_alpha.dmax[row][j];
-          const double x = x0 + c_alpha.la[row][j];
-          unsigned k = (unsigned)max(__double2loint(fma(x, inv_step, offm)), 0);
-          k = min(k, kclamp);
-          double c0, c1, c2, c3;
-          ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
-          const double y = fma(x, fma(x, fma(x, c0, c1), c2), c3);
-          if (inc) acc[j] += y;
-          if (COUNT) nterms += inc ? 1ull : 0ull;
+          for (int j = 0; j < NA; j++) {
+            if (j < jfull) continue;
+            if (j >= jany) break;
+            const bool inc = dq <= c_alpha.dmax[row][j];
+            const double x = xq + c_alpha.la[row][j];
+            unsigned k = (unsigned)max(__double2loint(fma(x, inv_step, offm)), 0);
+            k = min(k, kclamp);
+            double c0, c1, c2, c3;
+            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+            const double y = fma(x, fma(x, fma(x, c0, c1), c2), c3);
+            if (inc) acc[j] += y;
+            if (COUNT) nterms += inc ? 1ull : 0ull;
+          }
         }
       }
     }
@@ -240,36 +300,9 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
   if (WITHN && threadIdx.x == 0) R.nsum = S[kMaxFine];
 }
 
-// search_maxalpha sm-search.c:269-300 at one position
-template <bool COUNT>
-__device__ void dev_eval(const Params &P, const int *__restrict__ tkey, const int *__restrict__ tpos,
-                         const double *__restrict__ tnull, int chr, int pos, PtS &R,
-                         double (*red)[kMaxFine + 1], double *S, int *s_row, unsigned long long &nterms) {
-  if (threadIdx.x == 0) dev_init_point(P, chr, pos, R);
-  __syncthreads();
-  dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, R, kCoarse, red, S, nterms);
-  if (threadIdx.x == 0) {
-    // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
-    // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
-    // (scan-chromosome.c:97), whose fine interval is that of the last coarse value
-    int best = -1; double bs = -1.7976931348623157e308;
-    for (int j = 0; j < kCoarse; j++) if (S[j] > bs) { bs = S[j]; best = j; }
-    R.clr = bs; R.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
-    *s_row = best < 0 ? kCoarse - 1 : best;
-  }
-  __syncthreads();
-  const int row = *s_row;
-  dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, R, row, red, S, nterms);
-  if (threadIdx.x == 0) {
-    double bs = R.clr, la = R.lalpha;
-    const int nf = c_alpha.n[row];
-    for (int j = 0; j < nf; j++) if (S[j] > bs) { bs = S[j]; la = c_alpha.la[row][j]; }
-    R.lalpha = la; R.clr = 2.0 * bs;                // sm-search.c:298 without the null cancellation
-  }
-  __syncthreads();
-}
-
-// search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell)
+// search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell).
+// One copy of the evaluation code serves the two end points and every
+// bisection mid point (step 0, 1, 2...).
 template <bool COUNT>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks)
 scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tasks, OutPt *__restrict__ out,
@@ -279,28 +312,53 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
-  __shared__ int s_row, s_go;
+  __shared__ int s_row, s_next;
   const Task t = tasks[blockIdx.x];
   const int *__restrict__ tkey = tkey_all + (size_t)t.slot * P.n_pad;
   const int *__restrict__ tpos = tpos_all + (size_t)t.slot * P.n_pad;
   const double *__restrict__ tnull = tnull_all + (size_t)t.slot * (P.n_pad / kTile);
   unsigned long long nterms = 0;
 
-  dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, t.start_pos, A, red, S, &s_row, nterms);
-  if (!(flags & kFlagSingle)) {
-    dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, t.end_pos, B, red, S, &s_row, nterms);
-    for (;;) {
-      if (threadIdx.x == 0) s_go = (B.sweep_pos - A.sweep_pos > P.bp_resl);
-      __syncthreads();
-      if (!s_go) break;
-      dev_eval<COUNT>(P, tkey, tpos, tnull, t.chr, (A.sweep_pos + B.sweep_pos) / 2, M, red, S, &s_row, nterms);
-      if (threadIdx.x == 0) {
-        if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M; else A = M;   // scan-chromosome.c:116
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0 && !(A.clr > B.clr)) A = B;                  // scan-chromosome.c:110
+  int pos = t.start_pos;
+  for (int step = 0;; step++) {
+    // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
+    if (threadIdx.x == 0) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
+    dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, M, kCoarse, red, S, nterms);
+    if (threadIdx.x == 0) {
+      // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
+      // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
+      // (scan-chromosome.c:97), whose fine interval is that of the last coarse value
+      int best = -1; double bs = -1.7976931348623157e308;
+      for (int j = 0; j < kCoarse; j++) if (S[j] > bs) { bs = S[j]; best = j; }
+      M.clr = bs; M.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
+      s_row = best < 0 ? kCoarse - 1 : best;
+    }
+    __syncthreads();
+    const int row = s_row;
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, M, row, red, S, nterms);
+    if (threadIdx.x == 0) {
+      double bs = M.clr, la = M.lalpha;
+      const int nf = c_alpha.n[row];
+      for (int j = 0; j < nf; j++) if (S[j] > bs) { bs = S[j]; la = c_alpha.la[row][j]; }
+      M.lalpha = la; M.clr = 2.0 * bs;                // sm-search.c:298 without the null cancellation
+      // ---- search_maxpos bookkeeping ----
+      int next = -1;
+      if (step == 0) {
+        A = M;
+        if (!(flags & kFlagSingle)) next = t.end_pos;
+      } else {
+        if (step == 1) B = M;
+        else if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M;           // scan-chromosome.c:116
+        else A = M;
+        if (B.sweep_pos - A.sweep_pos > P.bp_resl) next = (A.sweep_pos + B.sweep_pos) / 2;
+        else if (!(A.clr > B.clr)) A = B;                              // scan-chromosome.c:110
+      }
+      s_next = next;
+    }
+    __syncthreads();
+    if (s_next < 0) break;
+    pos = s_next;
   }
   if (threadIdx.x == 0) {
     OutPt o;
@@ -366,31 +424,34 @@ permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, 
 // Class-bucketing of one genome instance: every tile of kTile consecutive sites
 // is sorted by (class, index) with a shared-memory bitonic network; the record
 // is key = class | index_in_tile << 20 plus the site's position.
-__global__ void __launch_bounds__(kTile / 2)
+constexpr int kBucketThreads = kTile / 2 < 1024 ? kTile / 2 : 1024;
+
+__global__ void __launch_bounds__(kBucketThreads)
 bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stride,
               const int *__restrict__ pos, const double *__restrict__ null_tab, int *__restrict__ tkey_all,
               int *__restrict__ tpos_all, double *__restrict__ tnull_all) {
   __shared__ unsigned keys[kTile];
-  __shared__ double wsum[kTile / 64];
+  __shared__ double wsum[kBucketThreads / 32];
   const int tile = blockIdx.x, slot = blockIdx.y;
   const int *cls = cls_all + (size_t)slot * cls_stride;
   const int base = tile * kTile;
-  for (int e = threadIdx.x; e < kTile; e += kTile / 2) {
+  for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
     const int gi = base + e;
     keys[e] = ((gi < n ? (unsigned)cls[gi] : 0u) << 12) | (unsigned)e;
   }
   __syncthreads();
   for (int k = 2; k <= kTile; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      const int t = threadIdx.x;
-      const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
-      const bool up = (lo & k) == 0;
-      const unsigned a = keys[lo], b = keys[hi];
-      if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      for (int t = threadIdx.x; t < kTile / 2; t += kBucketThreads) {
+        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
+        const bool up = (lo & k) == 0;
+        const unsigned a = keys[lo], b = keys[hi];
+        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
+      }
       __syncthreads();
     }
   int *tkey = tkey_all + (size_t)slot * n_pad, *tpos = tpos_all + (size_t)slot * n_pad;
-  for (int e = threadIdx.x; e < kTile; e += kTile / 2) {
+  for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
     const unsigned kk = keys[e];
     const int lidx = (int)(kk & 0xFFFu), gi = base + lidx;
     tkey[base + e] = (int)((kk >> 12) | ((unsigned)lidx << 20));
@@ -398,7 +459,7 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
   }
   // null log-likelihood of the tile (fixed tree; only complete tiles are ever read)
   double v = 0.0;
-  for (int e = threadIdx.x; e < kTile; e += kTile / 2)
+  for (int e = threadIdx.x; e < kTile; e += kBucketThreads)
     if (base + e < n) v += __ldg(null_tab + cls[base + e]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -406,7 +467,7 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
   __syncthreads();
   if (threadIdx.x == 0) {
     double tsum = 0.0;
-    for (int w = 0; w < kTile / 64; w++) tsum += wsum[w];
+    for (int w = 0; w < kBucketThreads / 32; w++) tsum += wsum[w];
     tnull_all[(size_t)slot * (n_pad / kTile) + tile] = tsum;
   }
 }
@@ -416,7 +477,7 @@ void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, cons
                    cudaStream_t s) {
   if (n_slots <= 0) return;
   dim3 grid(n_pad / kTile, n_slots);
-  bucket_kernel<<<grid, kTile / 2, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, tkey_all, tpos_all,
+  bucket_kernel<<<grid, kBucketThreads, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, tkey_all, tpos_all,
                                           tnull_all);
 }
 

@@ -21,9 +21,21 @@ namespace fscl {
 constexpr int kCoarse = 11;      // coarse alpha candidates (sm-search.c:276-282)
 constexpr int kMaxFine = 15;     // fine alpha candidates   (sm-search.c:284-296)
 constexpr int kRows = kCoarse + 1;  // fine lists for each coarse argmax + the coarse list (row 11)
-constexpr int kScanThreads = 256;
-constexpr int kScanMinBlocks = 3;   // 85 registers: the 15 fine-alpha accumulators do not spill
-constexpr int kTile = 2048;         // sites per class-bucketed tile (<= 4096: 12-bit index in the key)
+#ifndef FSCL_WARPS
+#define FSCL_WARPS 8
+#endif
+#ifndef FSCL_MINBLK
+#define FSCL_MINBLK 2
+#endif
+#ifndef FSCL_TILE
+#define FSCL_TILE 2048
+#endif
+#ifndef FSCL_KB
+#define FSCL_KB 4
+#endif
+constexpr int kScanThreads = FSCL_WARPS * 32;
+constexpr int kScanMinBlocks = FSCL_MINBLK;   // up to 128 registers: batch state + 15 fine-alpha accumulators stay in registers
+constexpr int kTile = FSCL_TILE;         // sites per class-bucketed tile (<= 4096: 12-bit index in the key)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kPermThreads = 1024;
 

@@ -65,7 +65,9 @@ assert PT_DTYPE.itemsize == 72
 EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy", "fscl_enum_cells",
            "fscl_grid_eval", "fscl_search_maxpos", "fscl_scan_chromosome", "fscl_block_permute",
            "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
-           "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak"]
+           "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak",
+           "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
+           "fscl_host_rng_draws"]
 
 _lib = None
 
@@ -98,6 +100,11 @@ def load_library(path=LIB_PATH):
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_reset_stats.argtypes = [vp]
     L.fscl_fp64_peak.argtypes = [ci, vp]
+    L.fscl_host_alpha_tables.argtypes = [vp, vp, vp, vp]
+    L.fscl_host_enum_cells.argtypes = [ci, vp, vp, ci, vp, vp, vp, ci]
+    L.fscl_host_gen_blocks.argtypes = [ci, vp, vp, vp, ci, vp, ci, vp]
+    L.fscl_host_replay_round.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp]
+    L.fscl_host_rng_draws.argtypes = [ci, C.c_uint64, C.c_uint32, C.c_uint32, ci, vp]
     _lib = L
     return L
 
@@ -116,6 +123,64 @@ def fp64_peak_tflops(device=0):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ---- host-side pieces of the path (no device needed) ---------------------------
+def host_alpha_tables(log_table=None):
+    """(la[12][15], dmax[12][15], n[12]); row 11 is the coarse list (sm-search.c:276-296)."""
+    L = load_library()
+    la = np.zeros((12, 15)); dmax = np.zeros((12, 15), dtype=np.int32); n = np.zeros(12, dtype=np.int32)
+    lt = None if log_table is None else np.ascontiguousarray(log_table, dtype=np.float64)
+    _check(L.fscl_host_alpha_tables(None if lt is None else lt.ctypes.data, la.ctypes.data, dmax.ctypes.data,
+                                    n.ctypes.data))
+    return la, dmax, n
+
+
+def host_enum_cells(chr_startpos, chr_bplen, G):
+    L = load_library()
+    sp, bl = _i32(chr_startpos), _i32(chr_bplen)
+    n = L.fscl_host_enum_cells(len(sp), sp.ctypes.data, bl.ctypes.data, G, None, None, None, 0)
+    if n < 0:
+        _check(2)
+    cc = np.zeros((3, max(n, 1)), dtype=np.int32)
+    L.fscl_host_enum_cells(len(sp), sp.ctypes.data, bl.ctypes.data, G, cc[0].ctypes.data, cc[1].ctypes.data,
+                           cc[2].ctypes.data, n)
+    return cc[:, :n]
+
+
+def host_gen_blocks(chr_, pos, t, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DEFAULT_SEED, max_blocks=1 << 16):
+    """(i, j, len) triples of permutation t (draw phase of snp_block_permute) and the D7 count."""
+    L = load_library()
+    chr_, pos = _i32(chr_), _i32(pos)
+    o = fscl_permute_opts_t(0, nbp, 1, width_mb, rng, seed, 1, 0, 1, 0)
+    blocks = np.zeros((max_blocks, 3), dtype=np.int32)
+    d7 = C.c_int32(0)
+    nb = L.fscl_host_gen_blocks(len(pos), chr_.ctypes.data, pos.ctypes.data, C.byref(o), t, blocks.ctypes.data,
+                                max_blocks, C.byref(d7))
+    if nb < 0:
+        _check(2)
+    return blocks[:min(nb, max_blocks)], d7.value
+
+
+def host_replay_round(pts, active, matrix, t_first, seed=DEFAULT_SEED, prune=1, permute_clr=None):
+    """Counting + stochastic pruning of one round; pts is updated in place."""
+    L = load_library()
+    active = _i32(active)
+    matrix = np.ascontiguousarray(matrix, dtype=np.float64)
+    o = fscl_permute_opts_t(0, 0.1, 1, 1.0, RNG_PHILOX, seed, prune, 0, 1, 0)
+    r = L.fscl_host_replay_round(pts.ctypes.data, active.ctypes.data, len(active), matrix.ctypes.data,
+                                 matrix.shape[0], t_first, C.byref(o),
+                                 None if permute_clr is None else permute_clr.ctypes.data)
+    if r < 0:
+        _check(2)
+    return r
+
+
+def host_rng_draws(rng, seed, n, t=0, stream=0):
+    L = load_library()
+    out = np.zeros(n, dtype=np.int32)
+    _check(L.fscl_host_rng_draws(rng, seed, t, stream, n, out.ctypes.data))
+    return out
 
 
 class Scanner:

@@ -215,25 +215,60 @@ void to_pt(const OutPt &o, fscl_pt_t &p) {
   p.permute_n = p.permute_p = p.permute_finished = 0; p.reserved = 0;
 }
 
-int enum_cells(const Ctx *c, int G, std::vector<Task> *out) {
+int enum_cells_raw(int n_chr, const int *startpos, const int *bplen, int G, std::vector<Task> *out) {
   // scan_thread's dispenser, scan-chromosome.c:178-205
   int chm = 0, n = 0;
-  if (c->n_chr == 0) return 0;
-  int pos = c->chr_startpos[0];
+  if (n_chr == 0) return 0;
+  int pos = startpos[0];
   for (;;) {
-    if (chm == c->n_chr) break;
-    if (pos >= c->chr_bplen[chm]) {
+    if (chm == n_chr) break;
+    if (pos >= bplen[chm]) {
       chm++;
-      if (chm == c->n_chr) break;
-      pos = c->chr_startpos[chm];
+      if (chm == n_chr) break;
+      pos = startpos[chm];
     }
     int s = pos, e = pos + G;
     pos += G;
-    if (e > c->chr_bplen[chm]) e = c->chr_bplen[chm];
+    if (e > bplen[chm]) e = bplen[chm];
     if (out) out->push_back(Task{0, chm, s, e, 0});
     n++;
   }
   return n;
+}
+int enum_cells(const Ctx *c, int G, std::vector<Task> *out) {
+  return enum_cells_raw(c->n_chr, c->chr_startpos.data(), c->chr_bplen.data(), G, out);
+}
+
+// Counting / stochastic pruning of one round, in permutation order
+// (scan-chromosome.c:488-498).  matrix is [R][n_active]; live[a] drops to 0
+// when a point finishes inside the round.  Returns permutations that scored.
+int replay_round(fscl_pt_t *pts, const int *active, size_t na, const double *matrix, int R, int t_first,
+                 DrawSource &src, int prune, float *permute_clr) {
+  std::vector<char> live(na, 1);
+  int scored = 0;
+  for (int r = 0; r < R; r++) {
+    const int t = t_first + r;
+    bool any = false;
+    for (size_t a = 0; a < na; a++) {
+      if (!live[a]) continue;
+      any = true;
+      fscl_pt_t &p = pts[active[a]];
+      const double clr = matrix[(size_t)r * na + a];
+      if (clr >= p.clr) {
+        p.permute_p++;
+        if (prune && p.permute_p >= FSCL_PRUNE_MIN_P) {                 // D6
+          int32_t u = src.prune_draw((uint32_t)t, (uint32_t)active[a]);
+          if (p.permute_p / (double)p.permute_n >= u / (2147483647 + 1.0)) { p.permute_finished = 1; live[a] = 0; }
+        }
+      }
+      if (permute_clr && p.permute_n < FSCL_NULL_SAVE)
+        permute_clr[(size_t)active[a] * FSCL_NULL_SAVE + p.permute_n] = (float)clr;
+      p.permute_n++;
+    }
+    if (!any) break;
+    scored++;
+  }
+  return scored;
 }
 
 // Draw phase of snp_block_permute (scan-chromosome.c:345-363).  Emits
@@ -241,11 +276,11 @@ int enum_cells(const Ctx *c, int G, std::vector<Task> *out) {
 // D7 (k > n_snps; the reference then indexes below the array) is DEFINED as
 // "shift the block so that it ends at n_snps" and counted.
 struct BlockGen {
-  const Ctx *c;
+  int n;
+  const int *pos;
+  const int *chr_end_index;      // per site: one past the last index of its chromosome
   double nbp, width_bp;
   int generate(DrawSource &src, std::vector<int4> &out, int *d7) const {
-    const int n = c->n;
-    const int *pos = c->h_pos.data();
     int i = 0, nb = 0;
     while (i < n) {
       int j = (int)(src.block_draw() / (2147483647 + 1.0) * n);
@@ -253,7 +288,7 @@ struct BlockGen {
       int k = j + (len < 2147483647.0 ? (int)len : 0x3FFFFFFF);
       if (k < n && k >= 0) {
         // while (k < n && chr[k]==chr[j] && pos[k]-pos[j] < width) k++  -- monotone, so search
-        int lim = c->chr_end_index[j];
+        int lim = chr_end_index[j];
         if (k < lim) {
           int lo = k, hi = lim;              // first index in [k, lim] failing pos[.]-pos[j] < width
           while (lo < hi) {
@@ -523,7 +558,7 @@ extern "C" int fscl_block_permute(void *ctx, const fscl_permute_opts_t *o, int t
   if (ensure_slots(c, 1)) return -1;
   DrawSource src;
   src.init(o->rng_kind, o->seed);
-  BlockGen gen{c, o->permute_nbp, o->scan_width_mb * 1e6};
+  BlockGen gen{c->n, c->h_pos.data(), c->chr_end_index.data(), o->permute_nbp, o->scan_width_mb * 1e6};
   std::vector<int4> blocks;
   int d7 = 0;
   if (src.sequential()) {
@@ -611,7 +646,7 @@ static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, i
   S.my_rows.clear();
   S.blocks.clear(); S.off.assign(1, 0);
   int d7 = 0;
-  BlockGen gen{c, o.permute_nbp, o.scan_width_mb * 1e6};
+  BlockGen gen{c->n, c->h_pos.data(), c->chr_end_index.data(), o.permute_nbp, o.scan_width_mb * 1e6};
   for (int r = 0; r < R; r++) {
     int t = S.t_next + r;
     bool mine = (t % S.stride) == o.first_perm;
@@ -667,30 +702,8 @@ static int perm_round_commit(Ctx *c, const double *d_matrix) {
   S.h_matrix.resize((size_t)S.R * na);
   CK(cudaMemcpyAsync(S.h_matrix.data(), dm, S.h_matrix.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  fscl_pt_t *pts = S.pts;
-  std::vector<char> live(na, 1);
-  for (int r = 0; r < S.R; r++) {                     // scan-chromosome.c:488-498, permutation order
-    const int t = S.t_next + r;
-    bool any = false;
-    for (size_t a = 0; a < na; a++) {
-      if (!live[a]) continue;
-      any = true;
-      fscl_pt_t &p = pts[S.active[a]];
-      const double clr = S.h_matrix[(size_t)r * na + a];
-      if (clr >= p.clr) {
-        p.permute_p++;
-        if (o.prune && p.permute_p >= FSCL_PRUNE_MIN_P) {               // D6
-          int32_t u = S.src.prune_draw((uint32_t)t, (uint32_t)S.active[a]);
-          if (p.permute_p / (double)p.permute_n >= u / (2147483647 + 1.0)) { p.permute_finished = 1; live[a] = 0; }
-        }
-      }
-      if (S.permute_clr && p.permute_n < FSCL_NULL_SAVE)
-        S.permute_clr[(size_t)S.active[a] * FSCL_NULL_SAVE + p.permute_n] = (float)clr;
-      p.permute_n++;
-    }
-    if (!any) break;
-    c->stats.n_scored++;
-  }
+  c->stats.n_scored += replay_round(S.pts, S.active.data(), na, S.h_matrix.data(), S.R, S.t_next, S.src, o.prune,
+                                    S.permute_clr);
   c->stats.n_rounds++;
   S.t_next += S.R;
   S.R = 0;
@@ -735,6 +748,84 @@ extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fsc
   return fscl_perm_end(c, stats_out);
 }
 
+// --------------------------------------------------------------------------- host-only entry points
+// These run without a device (tests exercise them on CPU-only machines); they are
+// the same code the GPU path uses for its host side.
+extern "C" int fscl_host_alpha_tables(const double *log_table, double *la, int32_t *dmax, int32_t *n) {
+  if (!la || !dmax || !n) return fail(FSCL_ERR_ARG, "bad argument");
+  std::vector<double> T(65536);
+  if (log_table) memcpy(T.data(), log_table, sizeof(double) * 65536);
+  else { T[0] = 0.0; for (int i = 1; i <= 0xFFFF; i++) T[i] = std::log((double)i); }
+  AlphaTables A;
+  build_alpha_tables(T.data(), A);
+  for (int r = 0; r < kRows; r++) {
+    n[r] = A.n[r];
+    for (int j = 0; j < kMaxFine; j++) { la[r * kMaxFine + j] = A.la[r][j]; dmax[r * kMaxFine + j] = A.dmax[r][j]; }
+  }
+  return FSCL_OK;
+}
+
+extern "C" int fscl_host_enum_cells(int n_chr, const int32_t *chr_startpos, const int32_t *chr_bplen, int G,
+                                    int32_t *cell_chr, int32_t *cell_start, int32_t *cell_end, int cap) {
+  if (n_chr <= 0 || !chr_startpos || !chr_bplen || G <= 0) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  std::vector<Task> cells;
+  int n = enum_cells_raw(n_chr, chr_startpos, chr_bplen, G, &cells);
+  for (int i = 0; i < n && i < cap; i++) {
+    if (cell_chr) cell_chr[i] = cells[i].chr;
+    if (cell_start) cell_start[i] = cells[i].start_pos;
+    if (cell_end) cell_end[i] = cells[i].end_pos;
+  }
+  return n;
+}
+
+// draw phase of snp_block_permute for permutation t: (i, j, len) triples
+extern "C" int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, const fscl_permute_opts_t *o,
+                                    int t, int32_t *blocks_out, int max_blocks, int32_t *d7_out) {
+  if (n_snps <= 0 || !chr || !pos || !o || t < 0 || o->permute_nbp <= 0) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  std::vector<int> cend(n_snps);
+  for (int i = n_snps - 1; i >= 0; i--) cend[i] = (i == n_snps - 1 || chr[i + 1] != chr[i]) ? i + 1 : cend[i + 1];
+  DrawSource src;
+  src.init(o->rng_kind, o->seed);
+  BlockGen gen{n_snps, pos, cend.data(), o->permute_nbp, o->scan_width_mb * 1e6};
+  std::vector<int4> blocks;
+  int d7 = 0;
+  if (src.sequential()) {
+    if (o->rng_kind != FSCL_RNG_LIBC) (void)src.block_draw();   // usleep burn, scan-chromosome.c:440
+    for (int q = 0; q <= t; q++) { blocks.clear(); gen.generate(src, blocks, &d7); }
+  } else {
+    src.set_perm((uint32_t)t);
+    gen.generate(src, blocks, &d7);
+  }
+  for (size_t b = 0; b < blocks.size() && blocks_out && (int)b < max_blocks; b++) {
+    blocks_out[3 * b] = blocks[b].x; blocks_out[3 * b + 1] = blocks[b].y; blocks_out[3 * b + 2] = blocks[b].z;
+  }
+  if (d7_out) *d7_out = d7;
+  return (int)blocks.size();
+}
+
+// counting + pruning of one round of R permutations starting at t_first
+// (Philox streams only: the pruning uniform is addressed by (t, scan point))
+extern "C" int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int n_active, const double *matrix,
+                                      int R, int t_first, const fscl_permute_opts_t *o, float *permute_clr) {
+  if (!pts || !active || n_active < 0 || !matrix || R < 0 || !o) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  if (o->rng_kind != FSCL_RNG_PHILOX) { fail(FSCL_ERR_ARG, "replay needs the counter-based stream"); return -1; }
+  DrawSource src;
+  src.init(o->rng_kind, o->seed);
+  return replay_round(pts, active, (size_t)n_active, matrix, R, t_first, src, o->prune, permute_clr);
+}
+
+// 31-bit draws of the two generators (known-answer tests)
+extern "C" int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out) {
+  if (!out || n < 0) return fail(FSCL_ERR_ARG, "bad argument");
+  if (rng_kind == FSCL_RNG_GLIBC) {
+    GlibcRand g; g.seed((unsigned)seed);
+    for (int i = 0; i < n; i++) out[i] = g.next();
+  } else if (rng_kind == FSCL_RNG_PHILOX) {
+    for (int i = 0; i < n; i++) out[i] = philox_draw(seed, t, stream, (uint32_t)i);
+  } else return fail(FSCL_ERR_ARG, "unknown generator");
+  return FSCL_OK;
+}
+
 // --------------------------------------------------------------------------- bench / stats
 extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
   Ctx *c = (Ctx *)ctx;
@@ -765,7 +856,7 @@ extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_ter
     ns = n_perm_slots;
     int rc = ensure_slots(c, ns); if (rc) return rc;
     DrawSource src; src.init(FSCL_RNG_PHILOX, 1);
-    BlockGen gen{c, 0.1, 1e6};
+    BlockGen gen{c->n, c->h_pos.data(), c->chr_end_index.data(), 0.1, 1e6};
     std::vector<int4> blocks; std::vector<int> off(1, 0);
     int d7 = 0;
     for (int q = 0; q < ns; q++) { src.set_perm((uint32_t)q); gen.generate(src, blocks, &d7); off.push_back((int)blocks.size()); }

@@ -131,6 +131,18 @@ int fscl_perm_begin(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opt
 int fscl_perm_round_score(void *ctx, double *d_matrix, int64_t cap, int *R_out, int *n_active_out);
 int fscl_perm_round_commit(void *ctx, const double *d_matrix);
 int fscl_perm_end(void *ctx, fscl_stats_t *stats);
+/* Host-side pieces of the path, callable without a device (same code the GPU
+ * path runs on the host): alpha candidate tables [12][15] (row 11 = coarse list,
+ * sm-search.c:276-296, with the per-alpha distance cut), cell enumeration, the
+ * draw phase of snp_block_permute, one round of counting/pruning, RNG draws. */
+int fscl_host_alpha_tables(const double *log_table, double *la, int32_t *dmax, int32_t *n);
+int fscl_host_enum_cells(int n_chr, const int32_t *chr_startpos, const int32_t *chr_bplen, int large_grid_sp,
+                         int32_t *cell_chr, int32_t *cell_start, int32_t *cell_end, int cap);
+int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, const fscl_permute_opts_t *opts,
+                         int t, int32_t *blocks, int max_blocks, int32_t *d7_hits);
+int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int n_active, const double *matrix,
+                           int R, int t_first, const fscl_permute_opts_t *opts, float *permute_clr);
+int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out);
 /* device-resident variants used by bench.py: time whole scans with inputs in HBM */
 int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_terms,
                     int64_t *terms_out, fscl_stats_t *stats);

@@ -422,3 +422,90 @@ def run_ref_exe(table, out_path, G=100000, n_permute=0, extra=(), threads=1, qui
         os.unlink(path)
     with open(out_path) as fh:
         return fh.read()
+
+
+# --------------------------------------------------------------------------
+# oracle-only problem preparation (no reference library needed)
+# --------------------------------------------------------------------------
+def load_snp_table_text(text, include_invariant=0, minimum_depth=5):
+    """Restatement of load_snp_input (snp-input.c:19-145) for well-formed input:
+    filters, folding to the minor count, first-seen depth and chromosome
+    indices, sort by (chromosome index, position)."""
+    names, chr_, pos, cnt, dep, fol = [], [], [], [], [], []
+    for line in text.splitlines():
+        line = line.strip()
+        if not line or line.startswith("#"):
+            continue
+        f = line.split()
+        if len(f) < 5:
+            continue
+        try:
+            p, k, d, fo = int(f[1]), int(f[2]), int(f[3]), int(f[4])
+        except ValueError:
+            continue
+        if d < minimum_depth:
+            continue
+        if not include_invariant and (k < 1 or k > d - 1):
+            continue
+        if f[0] not in names:
+            names.append(f[0])
+        if fo and k > d - k:
+            k = d - k
+        chr_.append(names.index(f[0])); pos.append(p); cnt.append(k); dep.append(d); fol.append(fo)
+    chr_, pos, cnt, dep, fol = (np.asarray(a, dtype=np.int32) for a in (chr_, pos, cnt, dep, fol))
+    depths = []
+    for d in dep:                       # first-seen order (snp-input.c:97-104), before the sort
+        if d not in depths:
+            depths.append(int(d))
+    order = np.lexsort((pos, chr_))     # stable; parity inputs have unique (chr, pos)
+    chr_, pos, cnt, dep, fol = (a[order] for a in (chr_, pos, cnt, dep, fol))
+    depth_p = np.array([depths.index(int(d)) for d in dep], dtype=np.int32)
+    return dict(chr_names=names, chr=chr_, pos=pos, obs_freq=cnt, depth_p=depth_p, folded=fol,
+                depths=np.array(depths, dtype=np.int32))
+
+
+def oracle_flatten(snp, asc_depth=0, asc_min_freq=1, ascbias_background_only=0, include_invariant=0,
+                   force_neutral=0, spline_pts=200):
+    """background_fsp -> compute_sweep_model_tables -> compute_snp_null_model with the
+    restatement only; returns the same dict as RefProblem.flatten()."""
+    L = lib()
+    depths = snp["depths"]
+    n_snps = len(snp["pos"])
+    fsp = [np.zeros(int(d) + 1) for d in depths]
+    ptrs = (C.c_void_p * len(depths))(*[f.ctypes.data for f in fsp])
+    of, dp, fo = (np.ascontiguousarray(snp[k], dtype=np.int32) for k in ("obs_freq", "depth_p", "folded"))
+    L.fo_background_fsp(n_snps, of.ctypes.data, dp.ctypes.data, fo.ctypes.data, len(depths), depths.ctypes.data,
+                        force_neutral, include_invariant, ptrs)
+    base = np.zeros(len(depths) + 1, dtype=np.int64)
+    for d in range(len(depths)):
+        base[d + 1] = base[d] + (depths[d] + 1) + (depths[d] // 2 + 1)
+    K = spline_pts
+    coef = np.zeros((int(base[-1]), K, 4))
+    null_tab = np.zeros(int(base[-1]))
+    for d in range(len(depths)):
+        n = int(depths[d])
+        cu, cf = np.zeros((n + 1, K, 4)), np.zeros((n // 2 + 1, K, 4))
+        L.fo_sweep_model_tables(fsp[d].ctypes.data, n, K, asc_depth, asc_min_freq, ascbias_background_only,
+                                include_invariant, cu.ctypes.data, cf.ctypes.data)
+        coef[base[d]:base[d] + n + 1] = cu
+        coef[base[d] + n + 1:base[d + 1]] = cf
+        nu, nf = np.zeros(n + 1), np.zeros(n // 2 + 1)
+        L.fo_null_model(fsp[d].ctypes.data, n, nu.ctypes.data, nf.ctypes.data)
+        null_tab[base[d]:base[d] + n + 1] = nu
+        null_tab[base[d] + n + 1:base[d + 1]] = nf
+    cls = np.where(fo != 0, base[dp] + depths[dp] + 1 + of, base[dp] + of).astype(np.int32)
+    chr_ = snp["chr"]
+    n_chr = len(snp["chr_names"])
+    start = np.array([int(np.argmax(chr_ == c)) for c in range(n_chr)], dtype=np.int32)
+    cnt = np.array([int((chr_ == c).sum()) for c in range(n_chr)], dtype=np.int32)
+    return dict(chr=np.ascontiguousarray(chr_), pos=np.ascontiguousarray(snp["pos"]), cls=cls,
+                chr_names=snp["chr_names"], chr_start=start, chr_nsnps=cnt,
+                chr_startpos=snp["pos"][start].astype(np.int32),
+                chr_bplen=snp["pos"][start + cnt - 1].astype(np.int32),
+                coef=coef, null_tab=null_tab, n_knots=K, step=24.0 / (K + 1.0), depths=depths, cls_base=base)
+
+
+def table_text(table):
+    names = table["chr_names"]
+    c, p, k, d, f = (table[x] for x in ("chr", "pos", "count", "depth", "folded"))
+    return "".join(f"{names[c[i]]}\t{p[i]}\t{k[i]}\t{d[i]}\t{f[i]}\n" for i in range(len(p)))

@@ -257,17 +257,23 @@ def main():
     if rank == 0 and not args.no_cpu_baseline:
         cells = enum_cells_host(flat)
         ncpu = len(os.sched_getaffinity(0))
-        k = max(ncpu, 8)
-        reference_cells_per_sec(rp, max(ncpu // 2, 2), ncpu, cells)
-        cps, cdt = reference_cells_per_sec(rp, 2 * k, ncpu, cells)
+        cps0, _ = reference_cells_per_sec(rp, max(ncpu, 8), ncpu, cells)          # calibration + warm-up
+        k = int(min(cells.shape[1], max(2 * ncpu, cps0 * 15.0)))                  # about 15 s of wall time
+        cps, cdt = reference_cells_per_sec(rp, k, ncpu, cells)
         cpu = {"value": cps / cells.shape[1], "unit": "scans/s", "cores": ncpu, "kind": "reference",
-               "sample": f"{2 * k} of {cells.shape[1]} cells of the forward scan, reference search_maxpos "
-                         f"on {ncpu} threads ({cdt:.1f} s)"}
+               "sample": f"{k} of {cells.shape[1]} cells of the forward scan (a permuted scan is the same work), "
+                         f"reference search_maxpos on {ncpu} threads, {cdt:.1f} s wall"}
     if rank == 0:
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
+            pass
+        traffic = None
+        try:      # DRAM bytes of this kernel from the committed ncu capture, scaled to this launch's task count
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r01_scan_kernel.json")))
+            traffic = prof["dram_bytes_per_task"] * R * n_cells
+        except (OSError, KeyError, ValueError):
             pass
         line = {
             "metric": "permuted_genome_scans_per_sec", "value": value, "unit": "scans/s", "n_gpus": world,
@@ -282,12 +288,14 @@ def main():
             "gpu_launches": int(st["score_launches"] + st["permute_launches"]),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp64_peak, "traffic": None,
+                         "frac": achieved_tf / fp64_peak, "traffic": traffic,
                          "kernel": "scan_cells_kernel", "kernel_ms": kern_ms, "snp_terms_per_launch": int(terms_round),
                          "flop_per_term": FLOP_PER_TERM,
                          "peak_source": "FP64 FMA-chain microbenchmark run in this process (MEASURED_PEAKS.json "
                                         "has no FP64 figure; SURVEY.md 8d)",
-                         "hbm_peak_gbs": peaks.get("hbm_gbs")},
+                         "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                         "hbm_algorithmic_bytes_per_launch": int(R * (flat["pos"].nbytes * 2) + flat["coef"].nbytes + 524288),
+                         "device_ms_per_step": (st["score_kernel_ms"] + st["permute_kernel_ms"]) / args.steps},
             "cpu_baseline": cpu,
         }
         line.update(extra)

@@ -65,7 +65,7 @@ assert PT_DTYPE.itemsize == 72
 EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy", "fscl_enum_cells",
            "fscl_grid_eval", "fscl_search_maxpos", "fscl_scan_chromosome", "fscl_block_permute",
            "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
-           "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak",
+           "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
            "fscl_host_rng_draws"]
 
@@ -100,6 +100,7 @@ def load_library(path=LIB_PATH):
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_reset_stats.argtypes = [vp]
     L.fscl_fp64_peak.argtypes = [ci, vp]
+    L.fscl_device_gen_blocks.argtypes = [vp, vp, ci, vp, ci, vp]
     L.fscl_host_alpha_tables.argtypes = [vp, vp, vp, vp]
     L.fscl_host_enum_cells.argtypes = [ci, vp, vp, ci, vp, vp, vp, ci]
     L.fscl_host_gen_blocks.argtypes = [ci, vp, vp, vp, ci, vp, ci, vp]
@@ -264,6 +265,16 @@ class Scanner:
         if nb < 0:
             _check(1)
         return cls, blocks[:min(nb, max_blocks)]
+
+    def device_gen_blocks(self, t, nbp=0.1, width_mb=1.0, seed=DEFAULT_SEED, max_blocks=1 << 16):
+        """(i, j, len) triples of permutation t drawn by the device kernel, and its flags."""
+        o = self.permute_opts(0, 1, nbp, width_mb, RNG_PHILOX, seed)
+        blocks = np.zeros((max_blocks, 3), dtype=np.int32)
+        flags = C.c_int32(0)
+        nb = self.L.fscl_device_gen_blocks(self._ctx, C.byref(o), t, blocks.ctypes.data, max_blocks, C.byref(flags))
+        if nb < 0:
+            _check(1)
+        return blocks[:min(nb, max_blocks)], flags.value
 
     def scan_permute(self, pts, n_permute, G, save_clr=False, **kw):
         pts = np.ascontiguousarray(pts.copy())

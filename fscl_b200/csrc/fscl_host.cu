@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -121,12 +122,15 @@ struct PermState {
   std::vector<double> h_matrix;
   double *d_matrix = nullptr;
   int t_next = 0, R = 0;
+  // device-resident rounds (Philox): counters, active list and pruning stay on the GPU
+  bool on_device = false;
+  int n_active = 0, cur = 0;           // d_active[cur] holds the active list
 };
 
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   Params P{};
   int n = 0, n_chr = 0, n_cls = 0;
   std::vector<int> h_chr, h_pos, h_cls, chr_start, chr_nsnps, chr_startpos, chr_bplen;
@@ -142,7 +146,16 @@ struct Ctx {
   int *d_pcls = nullptr, *d_scratch = nullptr;
   int *d_tkey = nullptr, *d_tpos = nullptr;       // permutation slots, class-bucketed
   int4 *d_blocks = nullptr; size_t blocks_cap = 0;
-  int *d_blkoff = nullptr;
+  int *d_blkoff = nullptr, *d_blkcnt = nullptr;
+  int *d_chr_end = nullptr;                        // per site: one past the last index of its chromosome
+  // device-resident permutation test state
+  int *d_active[2] = {nullptr, nullptr}, *d_pt_chr = nullptr, *d_pt_sweep = nullptr;
+  int *d_pp = nullptr, *d_pn = nullptr, *d_pf = nullptr;
+  double *d_pt_clr = nullptr;
+  float *d_pclr = nullptr;
+  int pts_cap = 0; bool pclr_alloc = false;
+  int *d_small = nullptr;                          // [5 * kSmall]: t_list, rows, flags, d7, scored ; + count
+  int small_cap = 0;
   Task *d_tasks = nullptr; OutPt *d_out = nullptr; size_t tasks_cap = 0;
   unsigned long long *d_terms = nullptr;
   std::vector<Task> h_tasks;
@@ -169,6 +182,8 @@ int ensure_slots(Ctx *c, int slots) {
   if (c->d_pcls) cudaFree(c->d_pcls);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->d_blkoff) cudaFree(c->d_blkoff);
+  if (c->d_blkcnt) cudaFree(c->d_blkcnt);
+  c->d_blkcnt = nullptr;
   if (c->d_tkey) cudaFree(c->d_tkey);
   if (c->d_tpos) cudaFree(c->d_tpos);
   if (c->d_tnull) cudaFree(c->d_tnull);
@@ -179,6 +194,7 @@ int ensure_slots(Ctx *c, int slots) {
   CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
+  CK(cudaMalloc(&c->d_blkcnt, (size_t)(slots + 1) * sizeof(int)));
   c->max_slots = slots;
   return FSCL_OK;
 }
@@ -404,6 +420,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  CK(cudaEventCreate(&c->ev2));
+  CK(cudaEventCreate(&c->ev3));
   CK(cudaMalloc(&c->d_pos, sizeof(int) * c->n));
   CK(cudaMalloc(&c->d_cls0, sizeof(int) * c->n));
   CK(cudaMalloc(&c->d_chr_start, sizeof(int) * c->n_chr));
@@ -419,6 +437,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMalloc(&c->d_logT, sizeof(double) * 65536));
   CK(cudaMalloc(&c->d_null, sizeof(double) * NC));
   CK(cudaMalloc(&c->d_terms, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_chr_end, sizeof(int) * c->n));
+  CK(cudaMemcpy(c->d_chr_end, c->chr_end_index.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemset(c->d_terms, 0, sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
@@ -452,8 +472,13 @@ extern "C" void fscl_destroy(void *ctx) {
   cudaFree(c->d_tile_lo); cudaFree(c->d_tile_hi); cudaFree(c->d_tkey); cudaFree(c->d_tpos); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
   cudaFree(c->d_pcls); cudaFree(c->d_scratch); cudaFree(c->d_blocks); cudaFree(c->d_blkoff);
   cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_matrix);
+  cudaFree(c->d_blkcnt); cudaFree(c->d_chr_end); cudaFree(c->d_active[0]); cudaFree(c->d_active[1]);
+  cudaFree(c->d_pt_chr); cudaFree(c->d_pt_sweep); cudaFree(c->d_pp); cudaFree(c->d_pn); cudaFree(c->d_pf);
+  cudaFree(c->d_pt_clr); cudaFree(c->d_pclr); cudaFree(c->d_small);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->ev3) cudaEventDestroy(c->ev3);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -530,13 +555,17 @@ static int upload_blocks(Ctx *c, const std::vector<int4> &blocks, const std::vec
   }
   if (!blocks.empty())
     CK(cudaMemcpyAsync(c->d_blocks, blocks.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+  std::vector<int> cnt(off.size(), 0);
+  for (size_t q = 0; q + 1 < off.size(); q++) cnt[q] = off[q + 1] - off[q];
   CK(cudaMemcpyAsync(c->d_blkoff, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_blkcnt, cnt.data(), cnt.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));          // cnt is a local
   return FSCL_OK;
 }
 
 static int apply_blocks(Ctx *c, int n_slots) {
   CK(cudaEventRecord(c->ev0, c->stream));
-  launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, n_slots, c->stream);
+  launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, n_slots, c->stream);
   CK(cudaGetLastError());
   launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull,
                 n_slots, c->stream);
@@ -580,6 +609,217 @@ extern "C" int fscl_block_permute(void *ctx, const fscl_permute_opts_t *o, int t
   return (int)blocks.size();
 }
 
+// ---- device-resident rounds (counter-based stream) ---------------------------------------------
+static int ensure_pts(Ctx *c, int n_pts, bool want_clr) {
+  if (n_pts > c->pts_cap) {
+    for (int *&p : {std::ref(c->d_active[0]), std::ref(c->d_active[1]), std::ref(c->d_pt_chr), std::ref(c->d_pt_sweep),
+                    std::ref(c->d_pp), std::ref(c->d_pn), std::ref(c->d_pf)}) { if (p) cudaFree(p); p = nullptr; }
+    if (c->d_pt_clr) cudaFree(c->d_pt_clr);
+    if (c->d_pclr) cudaFree(c->d_pclr);
+    c->d_pt_clr = nullptr; c->d_pclr = nullptr; c->pclr_alloc = false; c->pts_cap = 0;
+    const size_t b = sizeof(int) * (size_t)n_pts;
+    CK(cudaMalloc(&c->d_active[0], b)); CK(cudaMalloc(&c->d_active[1], b));
+    CK(cudaMalloc(&c->d_pt_chr, b)); CK(cudaMalloc(&c->d_pt_sweep, b));
+    CK(cudaMalloc(&c->d_pp, b)); CK(cudaMalloc(&c->d_pn, b)); CK(cudaMalloc(&c->d_pf, b));
+    CK(cudaMalloc(&c->d_pt_clr, sizeof(double) * (size_t)n_pts));
+    c->pts_cap = n_pts;
+  }
+  if (want_clr && !c->pclr_alloc) {
+    CK(cudaMalloc(&c->d_pclr, sizeof(float) * FSCL_NULL_SAVE * (size_t)c->pts_cap));
+    c->pclr_alloc = true;
+  }
+  return FSCL_OK;
+}
+
+static int ensure_small(Ctx *c, int n) {
+  if (n <= c->small_cap) return FSCL_OK;
+  if (c->d_small) cudaFree(c->d_small);
+  c->d_small = nullptr; c->small_cap = 0;
+  CK(cudaMalloc(&c->d_small, sizeof(int) * (5 * (size_t)n + 8)));
+  c->small_cap = n;
+  return FSCL_OK;
+}
+
+static int device_begin(Ctx *c) {
+  PermState &S = c->perm;
+  const int n = S.n_pts;
+  int rc = ensure_pts(c, std::max(n, 1), S.permute_clr != nullptr); if (rc) return rc;
+  std::vector<int> chr(n), sweep(n), pp(n), pn(n), pf(n), act;
+  std::vector<double> clr(n);
+  for (int i = 0; i < n; i++) {
+    const fscl_pt_t &p = S.pts[i];
+    chr[i] = p.chr; sweep[i] = p.sweep_pos; clr[i] = p.clr; pp[i] = p.permute_p; pn[i] = p.permute_n;
+    pf[i] = p.permute_finished;
+    if (!p.permute_finished) act.push_back(i);
+  }
+  const size_t b = sizeof(int) * (size_t)n;
+  if (n > 0) {
+    CK(cudaMemcpy(c->d_pt_chr, chr.data(), b, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pt_sweep, sweep.data(), b, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pp, pp.data(), b, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pn, pn.data(), b, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pf, pf.data(), b, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_pt_clr, clr.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice));
+    if (!act.empty()) CK(cudaMemcpy(c->d_active[0], act.data(), sizeof(int) * act.size(), cudaMemcpyHostToDevice));
+  }
+  S.cur = 0;
+  S.n_active = (int)act.size();
+  return FSCL_OK;
+}
+
+// One round with the whole loop body on the GPU: block draws, swap, bucketing, task list, search.
+static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, int *n_active_out) {
+  PermState &S = c->perm;
+  const fscl_permute_opts_t &o = S.o;
+  *R_out = 0;
+  if (n_active_out) *n_active_out = S.n_active;
+  if (S.n_active == 0 || S.t_next > o.n_permute) return FSCL_OK;
+  const size_t na = (size_t)S.n_active;
+  int R = o.round_perms > 0 ? o.round_perms
+                            : (int)std::min<size_t>(256, std::max<size_t>(S.stride, (16384 + na - 1) / na));
+  R = (R + S.stride - 1) / S.stride * S.stride;
+  const size_t slot_bytes = (size_t)c->n * 8;
+  const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);
+  R = std::min(R, mem_cap * S.stride);
+  R = std::min(R, o.n_permute - S.t_next + 1);
+  if (d_matrix && (int64_t)na > cap) return fail(FSCL_ERR_ARG, "clr matrix too small for one permutation");
+  if (d_matrix && (int64_t)R * (int64_t)na > cap) R = (int)std::max<int64_t>(1, cap / (int64_t)na);
+  std::vector<int> tl, rows;
+  for (int r = 0; r < R; r++)
+    if (((S.t_next + r) % S.stride) == o.first_perm) { tl.push_back(S.t_next + r); rows.push_back(r); }
+  const int ns = (int)tl.size();
+  double *dm = d_matrix;
+  if (!dm) {
+    const size_t need = (size_t)R * na;
+    if (need > c->matrix_cap) {
+      if (c->d_matrix) cudaFree(c->d_matrix);
+      c->d_matrix = nullptr; c->matrix_cap = 0;
+      CK(cudaMalloc(&c->d_matrix, need * sizeof(double)));
+      c->matrix_cap = need;
+    }
+    dm = c->d_matrix;
+  }
+  S.d_matrix = dm;
+  int rc = ensure_small(c, std::max(R, 1)); if (rc) return rc;
+  const int sc = c->small_cap;
+  int *d_tl = c->d_small, *d_rows = c->d_small + sc, *d_flags = c->d_small + 2 * sc, *d_d7 = c->d_small + 3 * sc;
+  if (ns < R) CK(cudaMemsetAsync(dm, 0, (size_t)R * na * sizeof(double), c->stream));
+  if (ns > 0) {
+    rc = ensure_slots(c, ns); if (rc) return rc;
+    const int stride = c->n / 4 + 1024;                       // block-list capacity per permutation
+    if ((size_t)ns * stride > c->blocks_cap) {
+      if (c->d_blocks) cudaFree(c->d_blocks);
+      c->d_blocks = nullptr; c->blocks_cap = 0;
+      CK(cudaMalloc(&c->d_blocks, (size_t)ns * stride * sizeof(int4)));
+      c->blocks_cap = (size_t)ns * stride;
+    }
+    CK(cudaMemcpyAsync(d_tl, tl.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_rows, rows.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    std::vector<int> starts(ns);
+    for (int q = 0; q < ns; q++) starts[q] = q * stride;
+    CK(cudaMemcpyAsync(c->d_blkoff, starts.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o.seed, d_tl, o.permute_nbp, o.scan_width_mb * 1e6, c->d_blocks,
+                      stride, c->d_blkcnt, d_flags, d_d7, ns, c->stream);
+    CK(cudaGetLastError());
+    std::vector<int> flags(ns), d7(ns), cnt(ns);
+    CK(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(d7.data(), d_d7, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), c->d_blkcnt, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    bool redo = false;
+    for (int q = 0; q < ns; q++) {
+      if (flags[q] & 6) redo = true;                          // ambiguous truncation or overflow: host draws
+      c->stats.d7_hits += d7[q];
+      c->stats.n_blocks += cnt[q];
+    }
+    if (redo) {
+      BlockGen gen{c->n, c->h_pos.data(), c->chr_end_index.data(), o.permute_nbp, o.scan_width_mb * 1e6};
+      std::vector<int4> blocks; std::vector<int> off(1, 0);
+      int dd = 0;
+      for (int q = 0; q < ns; q++) { S.src.set_perm((uint32_t)tl[q]); gen.generate(S.src, blocks, &dd); off.push_back((int)blocks.size()); }
+      rc = upload_blocks(c, blocks, off); if (rc) return rc;
+    }
+    launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, ns, c->stream);
+    CK(cudaGetLastError());
+    launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull, ns,
+                  c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    rc = ensure_tasks(c, (size_t)ns * na); if (rc) return rc;
+    launch_taskgen((int)na, ns, c->d_active[S.cur], d_rows, c->d_pt_chr, c->d_pt_sweep, o.large_grid_sp, c->d_tasks,
+                   c->stream);
+    CK(cudaGetLastError());
+    cudaEvent_t e2 = c->ev2, e3 = c->ev3;
+    CK(cudaEventRecord(e2, c->stream));
+    launch_scan(c->P, c->d_tasks, c->d_out, c->d_tkey, c->d_tpos, c->d_tnull, (int)((size_t)ns * na), 0, c->d_terms, dm,
+                c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e3, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.permute_kernel_ms += ms; c->stats.permute_launches++;
+    CK(cudaEventElapsedTime(&ms, e2, e3));
+    c->stats.score_kernel_ms += ms; c->stats.score_launches++;
+    c->stats.n_tasks += (int64_t)ns * (int64_t)na;
+    c->stats.n_grid_evals += (int64_t)ns * (int64_t)na;
+  } else {
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  S.R = R;
+  *R_out = R;
+  return FSCL_OK;
+}
+
+static int device_round_commit(Ctx *c, const double *d_matrix) {
+  PermState &S = c->perm;
+  const fscl_permute_opts_t &o = S.o;
+  const double *dm = d_matrix ? d_matrix : S.d_matrix;
+  const int sc = c->small_cap;
+  int *d_scored = c->d_small + 4 * sc, *d_count = c->d_small + 5 * sc;
+  CK(cudaMemsetAsync(d_scored, 0, sizeof(int) * S.R, c->stream));
+  launch_replay(S.n_active, S.R, S.t_next, c->d_active[S.cur], dm, c->d_pt_clr, c->d_pp, c->d_pn, c->d_pf,
+                S.permute_clr ? c->d_pclr : nullptr, o.seed, o.prune, d_scored, c->stream);
+  CK(cudaGetLastError());
+  launch_compact(S.n_active, c->d_active[S.cur], c->d_pf, c->d_active[S.cur ^ 1], d_count, c->stream);
+  CK(cudaGetLastError());
+  std::vector<int> scored(S.R);
+  int count = 0;
+  CK(cudaMemcpyAsync(scored.data(), d_scored, sizeof(int) * S.R, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  for (int r = 0; r < S.R; r++) c->stats.n_scored += scored[r];
+  S.cur ^= 1;
+  S.n_active = count;
+  c->stats.n_rounds++;
+  S.t_next += S.R;
+  S.R = 0;
+  return FSCL_OK;
+}
+
+static int device_end(Ctx *c) {
+  PermState &S = c->perm;
+  const int n = S.n_pts;
+  if (n == 0) return FSCL_OK;
+  std::vector<int> pp(n), pn(n), pf(n);
+  const size_t b = sizeof(int) * (size_t)n;
+  CK(cudaMemcpy(pp.data(), c->d_pp, b, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pn.data(), c->d_pn, b, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(pf.data(), c->d_pf, b, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) { S.pts[i].permute_p = pp[i]; S.pts[i].permute_n = pn[i]; S.pts[i].permute_finished = pf[i]; }
+  if (S.permute_clr) {
+    // only the entries written are meaningful (first permute_n, at most FSCL_NULL_SAVE)
+    std::vector<float> row(FSCL_NULL_SAVE);
+    for (int i = 0; i < n; i++) {
+      const int m = std::min(pn[i], FSCL_NULL_SAVE);
+      if (m > 0) CK(cudaMemcpy(S.permute_clr + (size_t)i * FSCL_NULL_SAVE, c->d_pclr + (size_t)i * FSCL_NULL_SAVE,
+                               sizeof(float) * m, cudaMemcpyDeviceToHost));
+    }
+  }
+  return FSCL_OK;
+}
+
 // Permutation test as rounds (scan_permute_thread scan-chromosome.c:412-546).
 // A round covers permutations [t_next, t_next+R).  Each rank scores the
 // permutations t with t % stride == first into rows of a device matrix
@@ -604,6 +844,13 @@ static int perm_begin(Ctx *c, fscl_pt_t *pts, int n_pts, const fscl_permute_opts
   for (int i = 0; i < n_pts; i++) S.active[i] = i;
   S.t_next = 0;
   S.open = true;
+  // counter-based stream: the loop body lives on the GPU (FSCL_B200_HOST_ROUNDS=1 keeps the host path)
+  const char *hr = getenv("FSCL_B200_HOST_ROUNDS");
+  S.on_device = !S.src.sequential() && !(hr && atoi(hr) != 0);
+  if (S.on_device) {
+    CK(cudaSetDevice(c->device));
+    return device_begin(c);
+  }
   return FSCL_OK;
 }
 
@@ -612,6 +859,7 @@ static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, i
   PermState &S = c->perm;
   if (!S.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
   CK(cudaSetDevice(c->device));
+  if (S.on_device) return device_round_score(c, d_matrix, cap, R_out, n_active_out);
   const fscl_permute_opts_t &o = S.o;
   const int G = o.large_grid_sp;
   fscl_pt_t *pts = S.pts;
@@ -696,6 +944,7 @@ static int perm_round_commit(Ctx *c, const double *d_matrix) {
   PermState &S = c->perm;
   if (!S.open || S.R <= 0) return fail(FSCL_ERR_ARG, "no scored round to commit");
   CK(cudaSetDevice(c->device));
+  if (S.on_device) return device_round_commit(c, d_matrix);
   const fscl_permute_opts_t &o = S.o;
   const size_t na = S.active.size();
   const double *dm = d_matrix ? d_matrix : S.d_matrix;
@@ -725,6 +974,11 @@ extern "C" int fscl_perm_round_commit(void *ctx, const double *d_matrix) {
 extern "C" int fscl_perm_end(void *ctx, fscl_stats_t *stats_out) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  if (c->perm.open && c->perm.on_device) {
+    CK(cudaSetDevice(c->device));
+    int rc = device_end(c);
+    if (rc) return rc;
+  }
   c->perm.open = false;
   if (stats_out) *stats_out = c->stats;
   return FSCL_OK;
@@ -746,6 +1000,39 @@ extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fsc
     if (rc) return rc;
   }
   return fscl_perm_end(c, stats_out);
+}
+
+// Block list of permutation t drawn ON THE DEVICE (gen_blocks_kernel); test hook.
+// flags: 1 D7, 2 ambiguous truncation, 4 overflow.
+extern "C" int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *o, int t, int32_t *blocks_out,
+                                      int max_blocks, int32_t *flags_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !o || t < 0 || o->rng_kind != FSCL_RNG_PHILOX) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { fail(FSCL_ERR_CUDA, "cudaSetDevice"); return -1; }
+  if (ensure_slots(c, 1) || ensure_small(c, 1)) return -1;
+  const int stride = c->n / 4 + 1024;
+  if ((size_t)stride > c->blocks_cap) {
+    if (c->d_blocks) cudaFree(c->d_blocks);
+    c->d_blocks = nullptr; c->blocks_cap = 0;
+    if (cudaMalloc(&c->d_blocks, (size_t)stride * sizeof(int4)) != cudaSuccess) { fail(FSCL_ERR_CUDA, "cudaMalloc"); return -1; }
+    c->blocks_cap = stride;
+  }
+  const int sc = c->small_cap;
+  int *d_tl = c->d_small, *d_flags = c->d_small + 2 * sc, *d_d7 = c->d_small + 3 * sc;
+  cudaMemcpy(d_tl, &t, sizeof(int), cudaMemcpyHostToDevice);
+  launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o->seed, d_tl, o->permute_nbp, o->scan_width_mb * 1e6, c->d_blocks,
+                    stride, c->d_blkcnt, d_flags, d_d7, 1, c->stream);
+  int cnt = 0, flags = 0;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail(FSCL_ERR_CUDA, "gen_blocks_kernel"); return -1; }
+  cudaMemcpy(&cnt, c->d_blkcnt, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost);
+  std::vector<int4> b(std::min(cnt, stride));
+  if (!b.empty()) cudaMemcpy(b.data(), c->d_blocks, sizeof(int4) * b.size(), cudaMemcpyDeviceToHost);
+  for (size_t q = 0; q < b.size() && blocks_out && (int)q < max_blocks; q++) {
+    blocks_out[3 * q] = b[q].x; blocks_out[3 * q + 1] = b[q].y; blocks_out[3 * q + 2] = b[q].z;
+  }
+  if (flags_out) *flags_out = flags;
+  return cnt;
 }
 
 // --------------------------------------------------------------------------- host-only entry points

@@ -392,13 +392,14 @@ void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *tkey
 // first delta originals land at a + r + delta*ceil((len-r)/delta).
 __global__ void __launch_bounds__(kPermThreads)
 permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, int *__restrict__ scratch_all,
-               const int4 *__restrict__ blocks, const int *__restrict__ blk_off) {
+               const int4 *__restrict__ blocks, const int *__restrict__ blk_start,
+               const int *__restrict__ blk_cnt) {
   const int slot = blockIdx.x;
   int *pc = pcls_all + (size_t)slot * n;
   int *sc = scratch_all + (size_t)slot * n;
   for (int i = threadIdx.x; i < n; i += kPermThreads) pc[i] = cls0[i];
   __syncthreads();
-  const int b0 = blk_off[slot], b1 = blk_off[slot + 1];
+  const int b0 = blk_start[slot], b1 = b0 + blk_cnt[slot];
   for (int b = b0; b < b1; b++) {
     const int4 blk = blocks[b];
     const int i = blk.x, j = blk.y, L = blk.z;
@@ -482,9 +483,163 @@ void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, cons
 }
 
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
-                    const int *blk_off, int n_slots, cudaStream_t s) {
+                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s) {
   if (n_slots <= 0) return;
-  permute_kernel<<<n_slots, kPermThreads, 0, s>>>(n, cls0, pcls_all, scratch_all, blocks, blk_off);
+  permute_kernel<<<n_slots, kPermThreads, 0, s>>>(n, cls0, pcls_all, scratch_all, blocks, blk_start, blk_cnt);
+}
+
+// ---------------------------------------------------------------------------
+// Counter-based stream on the device: Philox4x32-10, counter (idx, stream, t, 0), key = seed;
+// one 31-bit draw per call like rand() (same function as the host's DrawSource).
+__device__ __forceinline__ int dev_philox_draw(unsigned long long seed, unsigned t, unsigned stream, unsigned idx) {
+  unsigned c0 = idx, c1 = stream, c2 = t, c3 = 0u, k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return (int)(c0 >> 1);
+}
+
+// Draw phase of snp_block_permute (scan-chromosome.c:345-363) for one permutation per thread
+// block (the block list is inherently sequential: i advances by the length just drawn).
+// flags: 1 = D7 hit (defined behaviour, counted), 2 = a block length within rounding distance of
+// an integer (device log vs host log could truncate differently -> the host regenerates the
+// permutation), 4 = block list overflow (host regenerates).
+__global__ void gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ chr_end,
+                                  unsigned long long seed, const int *__restrict__ t_list, double nbp,
+                                  double width_bp, int4 *__restrict__ blocks, int stride,
+                                  int *__restrict__ counts, int *__restrict__ flags, int *__restrict__ d7) {
+  if (threadIdx.x != 0) return;
+  const int slot = blockIdx.x;
+  const unsigned t = (unsigned)t_list[slot];
+  int4 *out = blocks + (size_t)slot * stride;
+  unsigned ctr = 0;
+  int i = 0, nb = 0, flag = 0, nd7 = 0;
+  while (i < n) {
+    int j = (int)(dev_philox_draw(seed, t, 0, ctr++) / (2147483647 + 1.0) * n);
+    const double len = -1.0 / nbp * log(dev_philox_draw(seed, t, 0, ctr++) / (2147483647 + 1.0));
+    if (len < 2147483647.0 && fabs(len - rint(len)) <= 1e-9 * fmax(len, 1.0)) flag |= 2;
+    int k = j + (len < 2147483647.0 ? (int)len : 0x3FFFFFFF);
+    if (k < n && k >= 0) {
+      const int lim = chr_end[j];
+      if (k < lim) {
+        int lo = k, hi = lim;
+        const int pj = pos[j];
+        while (lo < hi) {
+          const int m = lo + (hi - lo) / 2;
+          if ((double)(pos[m] - pj) < width_bp) lo = m + 1; else hi = m;
+        }
+        k = lo;
+      }
+    }
+    if (i + (k - j) >= n) k = n;
+    if (k > n) { j = n - (k - j); k = n; nd7++; flag |= 1; }
+    const int L = min(k - j, n - i);
+    if (L > 0) {
+      if (nb < stride) out[nb] = make_int4(i, j, L, 0);
+      nb++;
+      i += L;
+    }
+  }
+  if (nb > stride) flag |= 4;
+  counts[slot] = nb; flags[slot] = flag; d7[slot] = nd7;
+}
+
+void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,
+                       double nbp, double width_bp, int4 *blocks, int stride, int *counts, int *flags, int *d7,
+                       int n_slots, cudaStream_t s) {
+  if (n_slots <= 0) return;
+  gen_blocks_kernel<<<n_slots, 32, 0, s>>>(n, pos, chr_end, seed, t_list, nbp, width_bp, blocks, stride, counts,
+                                           flags, d7);
+}
+
+// (permutation slot, active cell) -> search task; D4: the cell is re-derived from the observed
+// sweep position (scan-chromosome.c:481-486)
+__global__ void taskgen_kernel(int na, int ns, const int *__restrict__ active, const int *__restrict__ rows,
+                               const int *__restrict__ pt_chr, const int *__restrict__ pt_sweep, int G,
+                               Task *__restrict__ tasks) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+  if (a >= na || q >= ns) return;
+  const int s = active[a];
+  const int sp = pt_sweep[s], start = sp - (sp % G);
+  tasks[(size_t)q * na + a] = Task{q, pt_chr[s], start, start + G, (int)((size_t)rows[q] * na + a)};
+}
+
+void launch_taskgen(int na, int ns, const int *active, const int *rows, const int *pt_chr, const int *pt_sweep,
+                    int G, Task *tasks, cudaStream_t s) {
+  if (na <= 0 || ns <= 0) return;
+  dim3 grid((na + 255) / 256, ns);
+  taskgen_kernel<<<grid, 256, 0, s>>>(na, ns, active, rows, pt_chr, pt_sweep, G, tasks);
+}
+
+// Counting + stochastic pruning of a round, one thread per active cell, rows in permutation
+// order (scan-chromosome.c:488-498; D5, D6).  The pruning uniform is Philox(t, stream 1, cell).
+__global__ void replay_kernel(int na, int R, int t_first, const int *__restrict__ active,
+                              const double *__restrict__ matrix, const double *__restrict__ obs_clr,
+                              int *__restrict__ pp, int *__restrict__ pn, int *__restrict__ pf,
+                              float *__restrict__ permute_clr, unsigned long long seed, int prune,
+                              int *__restrict__ scored) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= na) return;
+  const int s = active[a];
+  const double obs = obs_clr[s];
+  int p = pp[s], n = pn[s], fin = 0;
+  for (int r = 0; r < R && !fin; r++) {
+    const double clr = matrix[(size_t)r * na + a];
+    if (scored[r] == 0) scored[r] = 1;                 // benign race: every writer stores 1
+    if (clr >= obs) {
+      p++;
+      if (prune && p >= 20) {
+        const int u = dev_philox_draw(seed, (unsigned)(t_first + r), 1, (unsigned)s);
+        if (p / (double)n >= u / (2147483647 + 1.0)) fin = 1;
+      }
+    }
+    if (permute_clr && n < 10000) permute_clr[(size_t)s * 10000 + n] = (float)clr;
+    n++;
+  }
+  pp[s] = p; pn[s] = n; pf[s] = fin;
+}
+
+void launch_replay(int na, int R, int t_first, const int *active, const double *matrix, const double *obs_clr,
+                   int *pp, int *pn, int *pf, float *permute_clr, unsigned long long seed, int prune, int *scored,
+                   cudaStream_t s) {
+  if (na <= 0 || R <= 0) return;
+  replay_kernel<<<(na + 255) / 256, 256, 0, s>>>(na, R, t_first, active, matrix, obs_clr, pp, pn, pf, permute_clr,
+                                                 seed, prune, scored);
+}
+
+// Order-preserving compaction of the active list (scan-chromosome.c:446-457): one CTA.
+__global__ void __launch_bounds__(1024) compact_kernel(int na, const int *__restrict__ active_in,
+                                                       const int *__restrict__ pf, int *__restrict__ active_out,
+                                                       int *__restrict__ count_out) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b = 0; b < na; b += 1024) {
+    const int a = b + threadIdx.x;
+    int s = 0, keep = 0;
+    if (a < na) { s = active_in[a]; keep = pf[s] == 0; }
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) wsum[warp] = __popc(m);
+    __syncthreads();
+    int off = base;
+    for (int w = 0; w < warp; w++) off += wsum[w];
+    if (keep) active_out[off + __popc(m & ((1u << lane) - 1u))] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += wsum[w]; base += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count_out = base;
+}
+
+void launch_compact(int na, const int *active_in, const int *pf, int *active_out, int *count_out, cudaStream_t s) {
+  compact_kernel<<<1, 1024, 0, s>>>(na, active_in, pf, active_out, count_out);
 }
 
 // ---------------------------------------------------------------------------

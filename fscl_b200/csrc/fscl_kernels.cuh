@@ -75,7 +75,16 @@ void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, cons
                    const double *null_tab, int *tkey_all, int *tpos_all, double *tnull_all, int n_slots,
                    cudaStream_t s);
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
-                    const int *blk_off, int n_slots, cudaStream_t s);
+                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s);
+void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,
+                       double nbp, double width_bp, int4 *blocks, int stride, int *counts, int *flags, int *d7,
+                       int n_slots, cudaStream_t s);
+void launch_taskgen(int na, int ns, const int *active, const int *rows, const int *pt_chr, const int *pt_sweep,
+                    int G, Task *tasks, cudaStream_t s);
+void launch_replay(int na, int R, int t_first, const int *active, const double *matrix, const double *obs_clr,
+                   int *pp, int *pn, int *pf, float *permute_clr, unsigned long long seed, int prune, int *scored,
+                   cudaStream_t s);
+void launch_compact(int na, const int *active_in, const int *pf, int *active_out, int *count_out, cudaStream_t s);
 void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);
 
 enum { kFlagSingle = 1,      // evaluate start_pos only (search_maxalpha at a point)

@@ -115,6 +115,11 @@ int fscl_scan_chromosome(void *ctx, int large_grid_sp, fscl_pt_t *out, int cap, 
  * up to max_blocks (i, j, len) triples. Returns #blocks or <0. Test hook. */
 int fscl_block_permute(void *ctx, const fscl_permute_opts_t *opts, int t, int32_t *cls_out,
                        int32_t *blocks, int max_blocks);
+/* The same draw phase executed by the device kernel (counter-based stream only); test hook.
+ * *flags: 1 = D7 hit, 2 = a length too close to an integer to trust the device log (the
+ * library then redraws on the host), 4 = block list overflow. */
+int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *opts, int t, int32_t *blocks,
+                           int max_blocks, int32_t *flags);
 /* scan_permute (scan-chromosome.c:582): pts in/out (permute_p/n/finished updated);
  * permute_clr = [n_pts][FSCL_NULL_SAVE] floats or NULL */
 int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *opts,

@@ -112,3 +112,40 @@ def test_round_size_invariance(api):
     c, _, _ = sc.scan_permute(obs, 50, G, rng=api.RNG_PHILOX, seed=5)
     for x in (b, c):
         assert np.array_equal(a["permute_p"], x["permute_p"]) and np.array_equal(a["permute_n"], x["permute_n"])
+
+
+@pytest.mark.parametrize("kind", ["small50", "genome", "dense", "mid100"])
+def test_device_block_draws_equal_host_and_oracle(api, kind):
+    """gen_blocks_kernel (Philox on the device) vs the host generator vs the oracle, bit for bit."""
+    import ctypes as C
+    tab, flat, G = problem(kind)
+    sc = api.Scanner(flat)
+    o = _oracle(flat)
+    g = o.rng("philox", 4242)
+    n = len(flat["pos"])
+    for t in (0, 1, 2, 17, 1000):
+        dev, flags = sc.device_gen_blocks(t, seed=4242)
+        host, d7 = api.host_gen_blocks(flat["chr"], flat["pos"], t, seed=4242)
+        assert not (flags & 6), "no ambiguous truncation / overflow expected"
+        assert np.array_equal(dev, host)
+        assert bool(flags & 1) == (d7 > 0)
+        o.L.fo_rng_set_perm(C.addressof(g), t)
+        _, wb, _ = o.block_permute(g)
+        want = wb.copy()
+        want[:, 2] = np.minimum(wb[:, 2] - wb[:, 1], n - wb[:, 0])
+        assert np.array_equal(dev, want)
+
+
+def test_device_rounds_equal_host_rounds(api, monkeypatch):
+    """Counting / pruning / compaction on the device vs the host replay of the same rounds."""
+    tab, flat, G = problem("small50")
+    sc = api.Scanner(flat)
+    obs = sc.scan_chromosome(G)
+    a, sta, ca = sc.scan_permute(obs, 70, G, rng=api.RNG_PHILOX, seed=11, save_clr=True)
+    monkeypatch.setenv("FSCL_B200_HOST_ROUNDS", "1")
+    sc.reset_stats()
+    b, stb, cb = sc.scan_permute(obs, 70, G, rng=api.RNG_PHILOX, seed=11, save_clr=True)
+    for k in ("permute_p", "permute_n", "permute_finished"):
+        assert np.array_equal(a[k], b[k])
+    assert np.array_equal(ca, cb)
+    assert sta["n_scored"] == stb["n_scored"] and a["permute_finished"].sum() > 0

@@ -664,7 +664,13 @@ static int device_begin(Ctx *c) {
   }
   S.cur = 0;
   S.n_active = (int)act.size();
-  return FSCL_OK;
+  // reserve the permutation slots once: rounds grow as cells are pruned, re-allocating on the way is slow
+  const size_t slot_bytes = (size_t)c->n * 16;
+  int want = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes));
+  want = std::min(want, S.o.n_permute + 1);
+  if (S.o.round_perms > 0) want = std::min(want, (S.o.round_perms + S.stride - 1) / S.stride);
+  else want = (want + S.stride - 1) / S.stride;
+  return ensure_slots(c, std::max(want, 1));
 }
 
 // One round with the whole loop body on the GPU: block draws, swap, bucketing, task list, search.
@@ -678,7 +684,7 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
   int R = o.round_perms > 0 ? o.round_perms
                             : (int)std::min<size_t>(256, std::max<size_t>(S.stride, (16384 + na - 1) / na));
   R = (R + S.stride - 1) / S.stride * S.stride;
-  const size_t slot_bytes = (size_t)c->n * 8;
+  const size_t slot_bytes = (size_t)c->n * 16;
   const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);
   R = std::min(R, mem_cap * S.stride);
   R = std::min(R, o.n_permute - S.t_next + 1);

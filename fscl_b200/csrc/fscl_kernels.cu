@@ -88,6 +88,53 @@ __device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, 
 #endif
 }
 
+// GS alphas of one record, all inside the cut: rows issued back to back, then the FMAs.
+template <int GS>
+__device__ __forceinline__ void group_terms(double *acc, const double *la, double xq, const char *crow,
+                                            double inv_step, double offm) {
+  double x[GS], c0[GS], c1[GS], c2[GS], c3[GS];
+#pragma unroll
+  for (int v = 0; v < GS; v++) {
+    x[v] = xq + la[v];
+    // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the integer in
+    // the low word; a knot one off at a boundary is harmless (C2 spline)
+    const unsigned k = (unsigned)__double2loint(fma(x[v], inv_step, offm));
+    ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[v], c1[v], c2[v], c3[v]);
+  }
+#pragma unroll
+  for (int v = 0; v < GS; v++) acc[v] += fma(x[v], fma(x[v], fma(x[v], c0[v], c1[v]), c2[v]), c3[v]);
+}
+
+// The common case (far tiles): the same GS <= 4 alphas for each of the KB records of a batch.
+// Two row buffers: the rows of record u+1 are in flight while record u is evaluated, so only the
+// first load of a batch is exposed.
+template <int GS, int KB>
+__device__ __forceinline__ void batch_terms_pipelined(double *acc, const double *la, const double (&x0)[KB],
+                                                      const char *const (&crow)[KB], double inv_step, double offm) {
+  double x[2][GS], c0[2][GS], c1[2][GS], c2[2][GS], c3[2][GS];
+#pragma unroll
+  for (int v = 0; v < GS; v++) {
+    x[0][v] = x0[0] + la[v];
+    const unsigned k = (unsigned)__double2loint(fma(x[0][v], inv_step, offm));
+    ld_row(reinterpret_cast<const double *>(crow[0] + (unsigned long long)k * 32ull), c0[0][v], c1[0][v], c2[0][v], c3[0][v]);
+  }
+#pragma unroll
+  for (int u = 0; u < KB; u++) {
+    const int b = u & 1, nb = b ^ 1;
+    if (u + 1 < KB) {
+#pragma unroll
+      for (int v = 0; v < GS; v++) {
+        x[nb][v] = x0[u + 1] + la[v];
+        const unsigned k = (unsigned)__double2loint(fma(x[nb][v], inv_step, offm));
+        ld_row(reinterpret_cast<const double *>(crow[u + 1] + (unsigned long long)k * 32ull), c0[nb][v], c1[nb][v],
+               c2[nb][v], c3[nb][v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < GS; v++) acc[v] += fma(x[b][v], fma(x[b][v], fma(x[b][v], c0[b][v], c1[b][v]), c2[b][v]), c3[b][v]);
+  }
+}
+
 // One pass over the window for the alpha list in c_alpha row `row`:
 // S[j] = sum over window sites with d <= dmax[j] of spline_cls(logt(d)+la[j]) - null
 // (sm_likelihood sm-search.c:105-150; the walks' "break at first exceed" equals
@@ -205,62 +252,58 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
         for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
       }
+      const char *crow[kB];
+      int dq[kB];
 #pragma unroll
       for (int u = 0; u < kB; u++) {
         const unsigned c = (unsigned)key[u] & 0xFFFFFu;
-        const char *crow = coef + (size_t)c * rowbytes;
-        asm("" : "+l"(crow));   // keep base + class offset in one register pair: row address = one IMAD.WIDE
-        int dq = d[u];
-        const double xq = x0[u];
+        crow[u] = coef + (size_t)c * rowbytes;
+        asm("" : "+l"(crow[u]));   // base + class offset in one register pair: row address = one IMAD.WIDE
+        dq[u] = d[u];
         if (!inside) {
           const int orig = t * kTile + (int)((unsigned)key[u] >> 20);
           const bool valid = (unsigned)(orig - ws) <= wlen;
-          if (!valid) dq = 0x7FFFFFFF;            // dmax tables are capped below INT_MAX
+          if (!valid) dq[u] = 0x7FFFFFFF;          // dmax tables are capped below INT_MAX
           if (WITHN && valid) accn += __ldg(P.null_tab + c);
         }
-        // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots).
-        // Groups of four issue their coefficient loads back to back before the FMAs.
+      }
+      // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots)
+      if (jfull > 0 && jfull <= 4) {
+        // far tiles: at most four alphas, rows double-buffered across the records of the batch
+        if (jfull == 4) batch_terms_pipelined<4, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
+        else if (jfull == 3) batch_terms_pipelined<3, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
+        else if (jfull == 2) batch_terms_pipelined<2, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
+        else batch_terms_pipelined<1, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
+        if (COUNT) nterms += (unsigned long long)(jfull * kB);
+      } else if (jfull > 4) {
 #pragma unroll
-        for (int g = 0; g < NA; g += 4) {
-          if (g >= jfull) break;
-          if (g + 4 <= NA && g + 4 <= jfull) {
-            double x[4], c0[4], c1[4], c2[4], c3[4];
+        for (int u = 0; u < kB; u++) {
 #pragma unroll
-            for (int v = 0; v < 4; v++) {
-              x[v] = xq + c_alpha.la[row][g + v];
-              // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the
-              // integer in the low word; a knot one off at a boundary is harmless (C2 spline)
-              const unsigned k = (unsigned)__double2loint(fma(x[v], inv_step, offm));
-              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[v], c1[v], c2[v], c3[v]);
-            }
-#pragma unroll
-            for (int v = 0; v < 4; v++) acc[g + v] += fma(x[v], fma(x[v], fma(x[v], c0[v], c1[v]), c2[v]), c3[v]);
-            if (COUNT) nterms += 4ull;
-          } else {
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-              if (g + v >= NA || g + v >= jfull) break;
-              const double x = xq + c_alpha.la[row][g + v];
-              const unsigned k = (unsigned)__double2loint(fma(x, inv_step, offm));
-              double c0, c1, c2, c3;
-              ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
-              acc[g + v] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
-              if (COUNT) nterms += 1ull;
-            }
+          for (int g = 0; g < NA; g += 4) {
+            if (g >= jfull) break;
+            const int gs = jfull - g;
+            if (g + 4 <= NA && gs >= 4) group_terms<4>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
+            else if (g + 3 <= NA && gs == 3) group_terms<3>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
+            else if (g + 2 <= NA && gs == 2) group_terms<2>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
+            else group_terms<1>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
           }
         }
-        // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
-        if (jany > jfull) {
+        if (COUNT) nterms += (unsigned long long)(jfull * kB);
+      }
+      // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+      if (jany > jfull) {
+#pragma unroll
+        for (int u = 0; u < kB; u++) {
 #pragma unroll
           for (int j = 0; j < NA; j++) {
             if (j < jfull) continue;
             if (j >= jany) break;
-            const bool inc = dq <= c_alpha.dmax[row][j];
-            const double x = xq + c_alpha.la[row][j];
+            const bool inc = dq[u] <= c_alpha.dmax[row][j];
+            const double x = x0[u] + c_alpha.la[row][j];
             unsigned k = (unsigned)max(__double2loint(fma(x, inv_step, offm)), 0);
             k = min(k, kclamp);
             double c0, c1, c2, c3;
-            ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+            ld_row(reinterpret_cast<const double *>(crow[u] + (unsigned long long)k * 32ull), c0, c1, c2, c3);
             const double y = fma(x, fma(x, fma(x, c0, c1), c2), c3);
             if (inc) acc[j] += y;
             if (COUNT) nterms += inc ? 1ull : 0ull;

@@ -67,7 +67,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
-           "fscl_host_rng_draws"]
+           "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf"]
 
 _lib = None
 
@@ -106,6 +106,8 @@ def load_library(path=LIB_PATH):
     L.fscl_host_gen_blocks.argtypes = [ci, vp, vp, vp, ci, vp, ci, vp]
     L.fscl_host_replay_round.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp]
     L.fscl_host_rng_draws.argtypes = [ci, C.c_uint64, C.c_uint32, C.c_uint32, ci, vp]
+    L.fscl_project_pvalues.argtypes = [ci, vp, vp, C.c_double, vp, vp]
+    L.fscl_ncx2_sf.argtypes = [ci, vp, C.c_double, vp, vp]
     _lib = L
     return L
 
@@ -175,6 +177,26 @@ def host_replay_round(pts, active, matrix, t_first, seed=DEFAULT_SEED, prune=1, 
     if r < 0:
         _check(2)
     return r
+
+
+def ncx2_sf(x, df, lam):
+    L = load_library()
+    x = np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
+    lam = np.ascontiguousarray(np.broadcast_to(lam, x.shape), dtype=np.float64)
+    out = np.zeros_like(x)
+    _check(L.fscl_ncx2_sf(len(x), x.ctypes.data, df, lam.ctypes.data, out.ctypes.data))
+    return out
+
+
+def project_pvalues(pts, permute_clr, df=2.0):
+    """Projected p-values (reference README.md:11; defined in DESIGN.md 3.6): (lambda_hat, p)."""
+    L = load_library()
+    pts = np.ascontiguousarray(pts)
+    clr = np.ascontiguousarray(permute_clr, dtype=np.float32)
+    assert clr.shape == (len(pts), NULL_SAVE)
+    lam, p = np.zeros(len(pts)), np.zeros(len(pts))
+    _check(L.fscl_project_pvalues(len(pts), pts.ctypes.data, clr.ctypes.data, df, lam.ctypes.data, p.ctypes.data))
+    return lam, p
 
 
 def host_rng_draws(rng, seed, n, t=0, stream=0):

@@ -1119,6 +1119,89 @@ extern "C" int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint
   return FSCL_OK;
 }
 
+// --------------------------------------------------------------------------- p-value projection
+// README.md:11 of the reference: "P-values are projected by estimating the non-centrality parameter of
+// the chisq distribution of twice the composite log-likelihood ratio and then estimating the integral
+// from the actual data CLR to infinity".  The reference never implemented it, so
+// this is a DEFINITION, not a port: df is fixed by the caller (default 2: sweep position and strength),
+// lambda = max(mean of the stored permuted CLRs - df, 0) (method of moments), p = P[ncx2(df, lambda) >= CLR].
+namespace {
+// regularised upper incomplete gamma Q(a, x), a > 0, x >= 0 (series below a+1, Lentz continued fraction above)
+double gamma_q(double a, double x) {
+  if (x <= 0.0) return 1.0;
+  const double lg = std::lgamma(a);
+  if (x < a + 1.0) {
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 0; n < 10000; n++) {
+      ap += 1.0; del *= x / ap; sum += del;
+      if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
+    }
+    return 1.0 - sum * std::exp(-x + a * std::log(x) - lg);
+  }
+  const double tiny = 1e-300;
+  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
+  for (int i = 1; i < 10000; i++) {
+    const double an = -i * (i - a);
+    b += 2.0;
+    d = an * d + b; if (std::fabs(d) < tiny) d = tiny;
+    c = b + an / c; if (std::fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    const double del = d * c;
+    h *= del;
+    if (std::fabs(del - 1.0) < 1e-16) break;
+  }
+  return std::exp(-x + a * std::log(x) - lg) * h;
+}
+
+// survival function of the non-central chi-square: Poisson(lambda/2) mixture of central ones,
+// summed outwards from the Poisson mode so that tiny tails keep their relative accuracy
+double ncx2_sf(double x, double df, double lambda) {
+  if (x <= 0.0) return 1.0;
+  if (lambda <= 0.0) return gamma_q(0.5 * df, 0.5 * x);
+  const double mu = 0.5 * lambda;
+  const int mode = (int)mu;
+  auto logpois = [&](int i) { return -mu + i * std::log(mu) - std::lgamma(i + 1.0); };
+  double total = 0.0;
+  double w = std::exp(logpois(mode));
+  double wi = w;
+  for (int i = mode; i < mode + 100000; i++) {          // upwards
+    const double term = wi * gamma_q(0.5 * df + i, 0.5 * x);
+    total += term;
+    if (i > mode && wi < 1e-18 * w && term < 1e-17 * total) break;
+    wi *= mu / (i + 1.0);
+  }
+  wi = w;
+  for (int i = mode - 1; i >= 0; i--) {                  // downwards
+    wi *= (i + 1.0) / mu;
+    const double term = wi * gamma_q(0.5 * df + i, 0.5 * x);
+    total += term;
+    if (wi < 1e-18 * w && term < 1e-17 * total) break;
+  }
+  return total > 1.0 ? 1.0 : total;
+}
+}  // namespace
+
+extern "C" int fscl_ncx2_sf(int n, const double *x, double df, const double *lambda, double *out) {
+  if (n < 0 || !x || !lambda || !out || !(df > 0)) return fail(FSCL_ERR_ARG, "bad argument");
+  for (int i = 0; i < n; i++) out[i] = ncx2_sf(x[i], df, lambda[i]);
+  return FSCL_OK;
+}
+
+extern "C" int fscl_project_pvalues(int n_pts, const fscl_pt_t *pts, const float *permute_clr, double df,
+                                    double *lambda_out, double *p_out) {
+  if (n_pts < 0 || (n_pts > 0 && (!pts || !permute_clr || !p_out)) || !(df > 0)) return fail(FSCL_ERR_ARG, "bad argument");
+  for (int i = 0; i < n_pts; i++) {
+    const int m = std::min(pts[i].permute_n, FSCL_NULL_SAVE);
+    double mean = 0.0;
+    for (int q = 0; q < m; q++) mean += (double)permute_clr[(size_t)i * FSCL_NULL_SAVE + q];
+    mean = m > 0 ? mean / m : 0.0;
+    const double lambda = std::max(mean - df, 0.0);
+    if (lambda_out) lambda_out[i] = lambda;
+    p_out[i] = m > 0 ? ncx2_sf(pts[i].clr, df, lambda) : 1.0;
+  }
+  return FSCL_OK;
+}
+
 // --------------------------------------------------------------------------- bench / stats
 extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
   Ctx *c = (Ctx *)ctx;

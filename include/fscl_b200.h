@@ -148,6 +148,12 @@ int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, con
 int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int n_active, const double *matrix,
                            int R, int t_first, const fscl_permute_opts_t *opts, float *permute_clr);
 int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out);
+/* p-value projection described at README.md:11 of the reference and never implemented there; host-only.
+ * DEFINITION: lambda = max(mean(stored permuted CLRs) - df, 0), p = P[ncx2(df, lambda) >= clr].
+ * permute_clr = [n_pts][FSCL_NULL_SAVE] as filled by fscl_scan_permute; lambda_out may be NULL. */
+int fscl_project_pvalues(int n_pts, const fscl_pt_t *pts, const float *permute_clr, double df,
+                         double *lambda_out, double *p_out);
+int fscl_ncx2_sf(int n, const double *x, double df, const double *lambda, double *out);
 /* device-resident variants used by bench.py: time whole scans with inputs in HBM */
 int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_terms,
                     int64_t *terms_out, fscl_stats_t *stats);

@@ -67,7 +67,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
-           "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf"]
+           "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library(path=LIB_PATH):
     L.fscl_host_rng_draws.argtypes = [ci, C.c_uint64, C.c_uint32, C.c_uint32, ci, vp]
     L.fscl_project_pvalues.argtypes = [ci, vp, vp, C.c_double, vp, vp]
     L.fscl_ncx2_sf.argtypes = [ci, vp, C.c_double, vp, vp]
+    L.fscl_build_tables.argtypes = [ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
     _lib = L
     return L
 
@@ -177,6 +178,24 @@ def host_replay_round(pts, active, matrix, t_first, seed=DEFAULT_SEED, prune=1, 
     if r < 0:
         _check(2)
     return r
+
+
+def build_tables(depths, fsp, spline_pts=200, asc_depth=0, asc_min_freq=1, ascbias_background_only=0,
+                 include_invariant=0, device=0):
+    """Sweep-model spline tables + null model on the GPU (compute_sweep_model_tables, sm-spline.c:486).
+    fsp: list of background spectra, one per depth.  Returns (coef[n_cls][K][4], null_tab[n_cls], flags)."""
+    L = load_library()
+    depths = _i32(depths)
+    fsp = [np.ascontiguousarray(f, dtype=np.float64) for f in fsp]
+    n_cls = int(sum((d + 1) + (d // 2 + 1) for d in depths))
+    coef = np.zeros((n_cls, spline_pts, 4))
+    null = np.zeros(n_cls)
+    ptrs = (C.c_void_p * len(fsp))(*[f.ctypes.data for f in fsp])
+    flags = C.c_int32(0)
+    _check(L.fscl_build_tables(device, len(depths), depths.ctypes.data, ptrs, spline_pts, asc_depth, asc_min_freq,
+                               ascbias_background_only, include_invariant, coef.ctypes.data, null.ctypes.data,
+                               C.byref(flags)))
+    return coef, null, flags.value
 
 
 def ncx2_sf(x, df, lam):

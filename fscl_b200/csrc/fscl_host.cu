@@ -30,6 +30,7 @@ static int fail(int code, const std::string &m) { g_err = m; return code; }
   } while (0)
 
 extern "C" const char *fscl_last_error(void) { return g_err.c_str(); }
+extern "C" int fscl_set_error(int code, const char *msg) { return fail(code, msg ? msg : ""); }
 
 extern "C" int fscl_device_count(void) {
   int n = 0;

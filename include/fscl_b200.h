@@ -148,6 +148,17 @@ int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, con
 int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int n_active, const double *matrix,
                            int R, int t_first, const fscl_permute_opts_t *opts, float *permute_clr);
 int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out);
+/* Sweep-model tables built on the device: compute_sweep_model_tables (sm-spline.c:486) with
+ * ascbias_adjust_background / ascbias_adjust_expect (asc-bias.c:27,97), pjh/pbk/p_kescape
+ * (sm-spline.c:337-445) and the natural-cubic-spline fit (sm-spline.c:63-220), plus the null model
+ * per class (scan-chromosome.c:23-37).  fsp[d] = background spectrum of depths[d] (depth+1 doubles,
+ * from background_fsp).  coef_out = [n_cls][spline_pts][4], null_out = [n_cls], class layout of
+ * fscl_problem_t.  *flags_out: 2 = vanishing-pivot rescue ran, 4 = a coefficient was zeroed
+ * (sm-spline.c:67-88, :107-111). */
+int fscl_build_tables(int device, int n_depths, const int32_t *depths, const double *const *fsp,
+                      int spline_pts, int asc_depth, int asc_min_freq, int ascbias_background_only,
+                      int include_invariant, double *coef_out, double *null_out, int32_t *flags_out);
+int fscl_set_error(int code, const char *msg);
 /* p-value projection described at README.md:11 of the reference and never implemented there; host-only.
  * DEFINITION: lambda = max(mean(stored permuted CLRs) - df, 0), p = P[ncx2(df, lambda) >= clr].
  * permute_clr = [n_pts][FSCL_NULL_SAVE] as filled by fscl_scan_permute; lambda_out may be NULL. */

@@ -582,9 +582,13 @@ static void ascbias_adjust_expect(double *p, int n, int min_obs, int d) {
 /* solve_linear_system sm-spline.c:63-118: unpivoted elimination restricted to a
  * band of 8, rows normalised, back substitution.  (The rescue branch for a
  * vanishing pivot :67-88 is restated too.) */
+static long fo_rescues = 0, fo_zeroed = 0;
+long fo_rescue_count(void) { return fo_rescues; }
+long fo_zeroed_count(void) { return fo_zeroed; }
 static void solve_band(double *b, double **m, double *v, int n) {
   for (int i = 0; i < n; i++) {
     if (fabs(m[i][i]) < 1e-20) {
+      fo_rescues++;
       int mx = i;
       for (int j = i + 1; j < n; j++)
         if (fabs(m[j][i]) > 0 && (mx == i || fabs(fabs(m[j][i]) - 1) < fabs(fabs(m[mx][i]) - 1))) mx = j;
@@ -602,7 +606,7 @@ static void solve_band(double *b, double **m, double *v, int n) {
     }
   }
   for (int i = n - 1; i >= 0; i--) {
-    if (fabs(m[i][i]) < 1e-10) { b[i] = 0; continue; }
+    if (fabs(m[i][i]) < 1e-10) { b[i] = 0; fo_zeroed++; continue; }
     b[i] = v[i];
     for (int k = i + 1; k < i + 8 && k < n; k++) b[i] -= m[i][k] * b[k];
   }

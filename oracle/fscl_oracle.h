@@ -122,6 +122,8 @@ void fo_sweep_model_tables(const double *fsp, int n, int spline_pts, int asc_dep
                            double *coef_unf /* [n+1][spline_pts][4] */,
                            double *coef_fold /* [n/2+1][spline_pts][4] */);
 void fo_estimate_spline(const double *x, const double *y, int n, double *coef /* [n][4] */);
+long fo_rescue_count(void);   /* times the vanishing-pivot branch (sm-spline.c:67-88) ran */
+long fo_zeroed_count(void);   /* coefficients zeroed in back substitution (sm-spline.c:107-111) */
 
 #ifdef __cplusplus
 }

@@ -210,6 +210,7 @@ int run_tasks(Ctx *c, bool permuted, int flags, bool fetch = true, double *d_clr
   CK(cudaEventRecord(c->ev0, c->stream));
   launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->d_tkey : c->d_tkey0, permuted ? c->d_tpos : c->d_tpos0,
               permuted ? c->d_tnull : c->d_tnull0, (int)nt, flags, c->d_terms, d_clr, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
   if (fetch) {
@@ -458,6 +459,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   P.pos = c->d_pos; P.chr_start = c->d_chr_start; P.chr_nsnps = c->d_chr_nsnps;
   P.coefC = c->d_coefC; P.row_doubles = (K + 2) * 4; P.tile_lo = c->d_tile_lo; P.tile_hi = c->d_tile_hi; P.logT = c->d_logT; P.null_tab = c->d_null;
   launch_bucket(c->n, c->n_pad, c->d_cls0, 0, c->d_pos, c->d_null, c->d_tkey0, c->d_tpos0, c->d_tnull0, 1, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
   *ctx_out = c;
@@ -567,9 +569,11 @@ static int upload_blocks(Ctx *c, const std::vector<int4> &blocks, const std::vec
 static int apply_blocks(Ctx *c, int n_slots) {
   CK(cudaEventRecord(c->ev0, c->stream));
   launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, n_slots, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull,
                 n_slots, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
   CK(cudaStreamSynchronize(c->stream));
@@ -728,6 +732,7 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
     CK(cudaEventRecord(c->ev0, c->stream));
     launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o.seed, d_tl, o.permute_nbp, o.scan_width_mb * 1e6, c->d_blocks,
                       stride, c->d_blkcnt, d_flags, d_d7, ns, c->stream);
+    c->stats.kernel_launches++;
     CK(cudaGetLastError());
     std::vector<int> flags(ns), d7(ns), cnt(ns);
     CK(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
@@ -748,19 +753,23 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
       rc = upload_blocks(c, blocks, off); if (rc) return rc;
     }
     launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, ns, c->stream);
+    c->stats.kernel_launches++;
     CK(cudaGetLastError());
     launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull, ns,
                   c->stream);
+    c->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, c->stream));
     rc = ensure_tasks(c, (size_t)ns * na); if (rc) return rc;
     launch_taskgen((int)na, ns, c->d_active[S.cur], d_rows, c->d_pt_chr, c->d_pt_sweep, o.large_grid_sp, c->d_tasks,
                    c->stream);
+    c->stats.kernel_launches++;
     CK(cudaGetLastError());
     cudaEvent_t e2 = c->ev2, e3 = c->ev3;
     CK(cudaEventRecord(e2, c->stream));
     launch_scan(c->P, c->d_tasks, c->d_out, c->d_tkey, c->d_tpos, c->d_tnull, (int)((size_t)ns * na), 0, c->d_terms, dm,
                 c->stream);
+    c->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(e3, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -788,8 +797,10 @@ static int device_round_commit(Ctx *c, const double *d_matrix) {
   CK(cudaMemsetAsync(d_scored, 0, sizeof(int) * S.R, c->stream));
   launch_replay(S.n_active, S.R, S.t_next, c->d_active[S.cur], dm, c->d_pt_clr, c->d_pp, c->d_pn, c->d_pf,
                 S.permute_clr ? c->d_pclr : nullptr, o.seed, o.prune, d_scored, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   launch_compact(S.n_active, c->d_active[S.cur], c->d_pf, c->d_active[S.cur ^ 1], d_count, c->stream);
+  c->stats.kernel_launches++;
   CK(cudaGetLastError());
   std::vector<int> scored(S.R);
   int count = 0;
@@ -1029,6 +1040,7 @@ extern "C" int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *o, i
   cudaMemcpy(d_tl, &t, sizeof(int), cudaMemcpyHostToDevice);
   launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o->seed, d_tl, o->permute_nbp, o->scan_width_mb * 1e6, c->d_blocks,
                     stride, c->d_blkcnt, d_flags, d_d7, 1, c->stream);
+  c->stats.kernel_launches++;
   int cnt = 0, flags = 0;
   if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail(FSCL_ERR_CUDA, "gen_blocks_kernel"); return -1; }
   cudaMemcpy(&cnt, c->d_blkcnt, sizeof(int), cudaMemcpyDeviceToHost);

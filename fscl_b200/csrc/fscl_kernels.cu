@@ -153,7 +153,7 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
 template <int NA, bool COUNT, bool WITHN>
 __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ tkey,
                                           const int *__restrict__ tpos, const double *__restrict__ tnull,
-                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
+                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S, int *s_tile,
                                           unsigned long long &nterms) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na_all = c_alpha.n[row];
@@ -174,19 +174,34 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const unsigned kclamp = (unsigned)P.n_knots + 1u;
     const double inv_step = P.inv_step, offm = P.off_magic;
     const int t0 = ws / kTile, t1 = we / kTile;
+    // ---- classify the tiles of the window once per pass, one thread per tile (shared table) ----
+    // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19
+    for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
+      const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+      const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
+      const int dfar = max(dlo, dhi);
+      const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
+      const int ins = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
+      int ja = 0, jf = 0;
+#pragma unroll
+      for (int j = 0; j < NA; j++) {
+        if (j < na && c_alpha.dmax[row][j] >= dnr) ja = j + 1;
+        if (j < na && c_alpha.dmax[row][j] >= dfar) jf = j + 1;
+      }
+      if (!ins) jf = 0;
+      // which branch of logt (sm-search.c:40-46) the whole tile takes: 2 = >>16, 1 = >>8, 0 = mixed
+      const int lu = (ins && dnr > 0xFFFFFF) ? 2 : ((ins && dnr > 0xFFFF && dfar <= 0xFFFFFF) ? 1 : 0);
+      const int needed = WITHN || ja > 0;
+      s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19);
+    }
+    __syncthreads();
     // tiles that can hold an admitted site: [ta, tb] (every tile when the null sum is wanted)
     int ta = t0, tb = t1;
     if (!WITHN) {
-      const int cut = c_alpha.dmax[row][0];          // widest cut of the list
       ta = 0x7FFFFFFF; tb = -1;
       for (int b0 = t0; b0 <= t1; b0 += 32) {
         const int t = b0 + lane;
-        bool hit = false;
-        if (t <= t1) {
-          const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
-          const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
-          hit = dnr <= cut;
-        }
+        const bool hit = t <= t1 && (s_tile[t - t0] >> 19);
         const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
         if (m) { ta = min(ta, b0 + __ffs(m) - 1); tb = max(tb, b0 + 31 - __clz(m)); }
       }
@@ -212,21 +227,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     for (int h = 0; h < n_batches; h++) {
       const int t = ta + h / HB;
       if (h % HB == 0) {
-        // per-tile alpha classification from the tile's position bounds (warp-uniform)
-        const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
-        const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
-        const int dfar = max(dlo, dhi);
-        const int dnr = (sweep < lo) ? lo - sweep : (sweep > hi ? sweep - hi : 0);
-        inside = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
-        jany = 0; jfull = 0;
-#pragma unroll
-        for (int j = 0; j < NA; j++) {
-          if (j < na && c_alpha.dmax[row][j] >= dnr) jany = j + 1;
-          if (j < na && c_alpha.dmax[row][j] >= dfar) jfull = j + 1;
-        }
-        if (!inside) jfull = 0;
-        // which branch of logt (sm-search.c:40-46) the whole tile takes: 2 = >>16, 1 = >>8, 0 = mixed
-        lut = (inside && dnr > 0xFFFFFF) ? 2 : ((inside && dnr > 0xFFFF && dfar <= 0xFFFFFF) ? 1 : 0);
+        const int info = s_tile[t - t0];
+        jany = info & 0xFF; jfull = (info >> 8) & 0xFF; inside = (info >> 16) & 1; lut = (info >> 17) & 3;
         if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
       }
       int key[kB], d[kB];
@@ -343,6 +345,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
   if (WITHN && threadIdx.x == 0) R.nsum = S[kMaxFine];
 }
 
+constexpr int kMaxTiles = (2 * 81920 + 1) / kTile + 3;   // tiles a window can touch (eval_range <= 81920)
+
 // search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell).
 // One copy of the evaluation code serves the two end points and every
 // bisection mid point (step 0, 1, 2...).
@@ -356,6 +360,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
   __shared__ int s_row, s_next;
+  __shared__ int s_tile[kMaxTiles];
   const Task t = tasks[blockIdx.x];
   const int *__restrict__ tkey = tkey_all + (size_t)t.slot * P.n_pad;
   const int *__restrict__ tpos = tpos_all + (size_t)t.slot * P.n_pad;
@@ -367,7 +372,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
     if (threadIdx.x == 0) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
-    dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, M, kCoarse, red, S, nterms);
+    dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, M, kCoarse, red, S, s_tile, nterms);
     if (threadIdx.x == 0) {
       // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
       // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
@@ -379,7 +384,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     }
     __syncthreads();
     const int row = s_row;
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, M, row, red, S, nterms);
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, M, row, red, S, s_tile, nterms);
     if (threadIdx.x == 0) {
       double bs = M.clr, la = M.lalpha;
       const int nf = c_alpha.n[row];

@@ -92,6 +92,7 @@ typedef struct {
   double score_kernel_ms;   /* CUDA-event time of the scan kernel, summed  */
   double permute_kernel_ms; /* CUDA-event time of the block-permute kernel */
   int64_t score_launches, permute_launches;
+  int64_t kernel_launches;  /* every kernel of this library launched for the context */
 } fscl_stats_t;
 
 const char *fscl_last_error(void);

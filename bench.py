@@ -228,9 +228,13 @@ def main():
         p, _, _ = s2.scan_permute(o, e2e_perms - 1, G, rng=api.RNG_PHILOX, seed=2, prune=0)
         s2.close()
         return p
-    h2d = sum(flat[k].nbytes for k in ("chr", "pos", "cls", "coef", "null_tab")) + 65536 * 8 + \
-        (1 + e2e_perms) * n_cells * 20
-    d2h = n_cells * 48 + e2e_perms * n_cells * 8
+    # bytes that cross PCIe per step, counted from the buffers the library copies:
+    #   in : the problem (sites, classes, spline table, null table), the log table, the cell task list,
+    #        the scan points handed to the permutation test (chr, sweep_pos, clr, counters)
+    #   out: 56-byte result per cell of the forward scan, 3 counters per cell, n_active + flags per round
+    h2d = sum(flat[k].nbytes for k in ("chr", "pos", "cls", "coef", "null_tab")) + 65536 * 8 + n_cells * 20 + \
+        n_cells * (5 * 4 + 8)
+    d2h = n_cells * 56 + n_cells * 12 + 64
     e2e_step()
     barrier()
     t0 = time.perf_counter()

@@ -403,3 +403,16 @@ def format_records(pts, chr_names, pos, n_permute=0, label=None, maximum_only=Fa
         else:
             out.append(f"{head}\t{p['n_snps']}\t{pos[p['window_start']]}\t{pos[p['window_end']]}\n")
     return "".join(out)
+
+
+def format_nulldist(pts, chr_names, permute_clr):
+    """`<out>-nulldist` companion file (scan-chromosome.c:753-796): header with the 10 000 quantile
+    labels, then per cell the stored permuted CLRs sorted ascending as %1.2f."""
+    head = "chr\tpos\tCLR\talpha\tp\tn" + "".join("\t%1.4f" % (j / float(NULL_SAVE)) for j in range(NULL_SAVE)) + "\n"
+    out = [head]
+    for i, p in enumerate(pts):
+        m = min(int(p["permute_n"]), NULL_SAVE)
+        vals = np.sort(np.asarray(permute_clr[i, :m], dtype=np.float32))
+        out.append(f"{chr_names[p['chr']]}\t{p['sweep_pos']}\t{'%1.3f' % p['clr']}\t{'%1.3e' % math.exp(p['lalpha'])}"
+                   f"\t{p['permute_p']}\t{p['permute_n']}" + "".join("\t%1.2f" % float(v) for v in vals) + "\n")
+    return "".join(out)

@@ -49,7 +49,7 @@ class fscl_permute_opts_t(C.Structure):
 class fscl_stats_t(C.Structure):
     _fields_ = [("n_scored", C.c_int64), ("n_tasks", C.c_int64), ("n_grid_evals", C.c_int64),
                 ("n_rounds", C.c_int64), ("n_blocks", C.c_int64), ("d7_hits", C.c_int32),
-                ("reserved", C.c_int32), ("score_kernel_ms", C.c_double), ("permute_kernel_ms", C.c_double),
+                ("bound_failures", C.c_int32), ("score_kernel_ms", C.c_double), ("permute_kernel_ms", C.c_double),
                 ("score_launches", C.c_int64), ("permute_launches", C.c_int64),
                 ("kernel_launches", C.c_int64)]
 
@@ -68,7 +68,8 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_scan_permute", "fscl_perm_begin", "fscl_perm_round_score", "fscl_perm_round_commit",
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
-           "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error"]
+           "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
+           "fscl_set_exact_candidates"]
 
 _lib = None
 
@@ -99,6 +100,7 @@ def load_library(path=LIB_PATH):
     L.fscl_perm_end.argtypes = [vp, vp]
     L.fscl_bench_scan.argtypes = [vp, ci, ci, ci, vp, vp]
     L.fscl_get_stats.argtypes = [vp, vp]
+    L.fscl_set_exact_candidates.argtypes = [vp, ci]
     L.fscl_reset_stats.argtypes = [vp]
     L.fscl_fp64_peak.argtypes = [ci, vp]
     L.fscl_device_gen_blocks.argtypes = [vp, vp, ci, vp, ci, vp]
@@ -358,6 +360,11 @@ class Scanner:
         st = fscl_stats_t()
         _check(self.L.fscl_bench_scan(self._ctx, G, n_perm_slots, int(count_terms), C.byref(terms), C.byref(st)))
         return terms.value, st.asdict()
+
+    def set_exact_candidates(self, on=True):
+        """on: evaluate every coarse alpha candidate site by site (no pruning by bounds); results are
+        identical either way (fscl_b200.h), only the work differs."""
+        _check(self.L.fscl_set_exact_candidates(self._ctx, 1 if on else 0))
 
     def stats(self):
         st = fscl_stats_t()

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -140,12 +141,12 @@ struct Ctx {
   int *d_pos = nullptr, *d_cls0 = nullptr, *d_chr_start = nullptr, *d_chr_nsnps = nullptr;
   double *d_coefC = nullptr, *d_logT = nullptr, *d_null = nullptr;
   int n_pad = 0;
-  int *d_tkey0 = nullptr, *d_tpos0 = nullptr;     // observed genome, class-bucketed
-  double *d_tnull0 = nullptr, *d_tnull = nullptr; // per-tile null sums (observed / slots)
+  TileSet ts0{}, ts{};                            // observed genome / permutation slots, class-bucketed
+  double *d_pmax = nullptr;                       // piece maxima for the candidate bounds
+  bool no_prune = false;                          // evaluate every coarse candidate exactly
   int *d_tile_lo = nullptr, *d_tile_hi = nullptr;
   int max_slots = 0;
   int *d_pcls = nullptr, *d_scratch = nullptr;
-  int *d_tkey = nullptr, *d_tpos = nullptr;       // permutation slots, class-bucketed
   int4 *d_blocks = nullptr; size_t blocks_cap = 0;
   int *d_blkoff = nullptr, *d_blkcnt = nullptr;
   int *d_chr_end = nullptr;                        // per site: one past the last index of its chromosome
@@ -178,6 +179,60 @@ int ensure_tasks(Ctx *c, size_t n) {
   return FSCL_OK;
 }
 
+// Upper bound of every spline piece (null already folded into c3) over the x interval its knot
+// index stands for on the device: knot k < K covers [-20 + k step, -20 + (k+1) step), the two
+// clamp rows K, K+1 repeat piece K-1 (sm-spline.c:53) up to x = 4 and one step beyond.  End
+// points, interior critical points, plus a margin far above the rounding of a Horner evaluation.
+// A piece with a non-finite coefficient (D14) gets +inf: its candidates are never pruned.
+void build_piece_maxima(const double *coefC, int NC, int K, double step, std::vector<double> &pmax) {
+  pmax.assign((size_t)NC * (K + 2), 0.0);
+  for (int cl = 0; cl < NC; cl++)
+    for (int k = 0; k < K + 2; k++) {
+      const double *q = coefC + ((size_t)cl * (K + 2) + k) * 4;
+      const double c0 = q[0], c1 = q[1], c2 = q[2], c3 = q[3];
+      double &out = pmax[(size_t)cl * (K + 2) + k];
+      if (!(std::isfinite(c0) && std::isfinite(c1) && std::isfinite(c2) && std::isfinite(c3))) {
+        out = std::numeric_limits<double>::infinity();
+        continue;
+      }
+      const double a = -20.0 + k * step - 1e-9, b = -20.0 + (k + 1) * step + 1e-9;
+      auto f = [&](double x) { return x * (x * (x * c0 + c1) + c2) + c3; };
+      double m = std::max(f(a), f(b));
+      const double qa = 3.0 * c0, qb = 2.0 * c1, qc = c2;          // f'(x) = qa x^2 + qb x + qc
+      if (qa != 0.0) {
+        const double disc = qb * qb - 4.0 * qa * qc;
+        if (disc >= 0.0) {
+          const double sq = std::sqrt(disc);
+          for (int sg = -1; sg <= 1; sg += 2) {
+            const double r = (-qb + sg * sq) / (2.0 * qa);
+            if (r > a && r < b) m = std::max(m, f(r));
+          }
+        }
+      } else if (qb != 0.0) {
+        const double r = -qc / qb;
+        if (r > a && r < b) m = std::max(m, f(r));
+      }
+      for (int i = 1; i < 8; i++) m = std::max(m, f(a + (b - a) * i / 8.0));   // belt and braces
+      const double xm = std::max(std::fabs(a), std::fabs(b));
+      const double mag = std::fabs(c3) + xm * (std::fabs(c2) + xm * (std::fabs(c1) + xm * std::fabs(c0)));
+      out = m + 1e-11 * mag + 1e-300;
+    }
+}
+
+void free_tiles(TileSet &t) {
+  cudaFree(t.key); cudaFree(t.pos); cudaFree(t.tnull); cudaFree(t.run); cudaFree(t.nrun);
+  t = TileSet{};
+}
+
+int alloc_tiles(TileSet &t, int slots, int n_pad) {
+  CK(cudaMalloc(&t.tnull, (size_t)slots * (n_pad / kTile) * sizeof(double)));
+  CK(cudaMalloc(&t.nrun, (size_t)slots * (n_pad / kTile) * sizeof(int)));
+  CK(cudaMalloc(&t.key, (size_t)slots * n_pad * sizeof(int)));
+  CK(cudaMalloc(&t.pos, (size_t)slots * n_pad * sizeof(int)));
+  CK(cudaMalloc(&t.run, (size_t)slots * n_pad * sizeof(int)));
+  return FSCL_OK;
+}
+
 int ensure_slots(Ctx *c, int slots) {
   if (slots <= c->max_slots) return FSCL_OK;
   if (c->d_pcls) cudaFree(c->d_pcls);
@@ -185,13 +240,9 @@ int ensure_slots(Ctx *c, int slots) {
   if (c->d_blkoff) cudaFree(c->d_blkoff);
   if (c->d_blkcnt) cudaFree(c->d_blkcnt);
   c->d_blkcnt = nullptr;
-  if (c->d_tkey) cudaFree(c->d_tkey);
-  if (c->d_tpos) cudaFree(c->d_tpos);
-  if (c->d_tnull) cudaFree(c->d_tnull);
-  c->d_pcls = c->d_scratch = c->d_blkoff = c->d_tkey = c->d_tpos = nullptr; c->d_tnull = nullptr; c->max_slots = 0;
-  CK(cudaMalloc(&c->d_tnull, (size_t)slots * (c->n_pad / kTile) * sizeof(double)));
-  CK(cudaMalloc(&c->d_tkey, (size_t)slots * c->n_pad * sizeof(int)));
-  CK(cudaMalloc(&c->d_tpos, (size_t)slots * c->n_pad * sizeof(int)));
+  free_tiles(c->ts);
+  c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
+  { int rc = alloc_tiles(c->ts, slots, c->n_pad); if (rc) return rc; }
   CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
@@ -208,8 +259,8 @@ int run_tasks(Ctx *c, bool permuted, int flags, bool fetch = true, double *d_clr
   if (rc) return rc;
   CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev0, c->stream));
-  launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->d_tkey : c->d_tkey0, permuted ? c->d_tpos : c->d_tpos0,
-              permuted ? c->d_tnull : c->d_tnull0, (int)nt, flags, c->d_terms, d_clr, c->stream);
+  launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->ts : c->ts0, (int)nt, flags | (c->no_prune ? kFlagNoPrune : 0),
+              c->d_terms, d_clr, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, c->stream));
@@ -410,6 +461,9 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
       double *d = coefC.data() + ((size_t)cl * (K + 2) + k) * 4;
       d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3] - p->null_tab[cl];
     }
+  std::vector<double> pmax;
+  build_piece_maxima(coefC.data(), NC, K, p->step, pmax);
+  c->no_prune = getenv("FSCL_B200_NO_PRUNE") != nullptr;
   c->n_pad = (c->n + kTile - 1) / kTile * kTile;
   const int n_tiles = c->n_pad / kTile;
   std::vector<int> tlo(n_tiles), thi(n_tiles);
@@ -429,19 +483,19 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMalloc(&c->d_chr_start, sizeof(int) * c->n_chr));
   CK(cudaMalloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
   CK(cudaMalloc(&c->d_coefC, sizeof(double) * coefC.size()));
-  CK(cudaMalloc(&c->d_tkey0, sizeof(int) * c->n_pad));
-  CK(cudaMalloc(&c->d_tpos0, sizeof(int) * c->n_pad));
-  CK(cudaMalloc(&c->d_tnull0, sizeof(double) * n_tiles));
+  { int rc = alloc_tiles(c->ts0, 1, c->n_pad); if (rc) return rc; }
+  CK(cudaMalloc(&c->d_pmax, sizeof(double) * pmax.size()));
+  CK(cudaMemcpy(c->d_pmax, pmax.data(), sizeof(double) * pmax.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_tile_lo, sizeof(int) * n_tiles));
   CK(cudaMalloc(&c->d_tile_hi, sizeof(int) * n_tiles));
   CK(cudaMemcpy(c->d_tile_lo, tlo.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_tile_hi, thi.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_logT, sizeof(double) * 65536));
   CK(cudaMalloc(&c->d_null, sizeof(double) * NC));
-  CK(cudaMalloc(&c->d_terms, sizeof(unsigned long long)));
+  CK(cudaMalloc(&c->d_terms, 2 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
   CK(cudaMalloc(&c->d_chr_end, sizeof(int) * c->n));
   CK(cudaMemcpy(c->d_chr_end, c->chr_end_index.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
-  CK(cudaMemset(c->d_terms, 0, sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_terms, 0, 2 * sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_chr_start, c->chr_start.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
@@ -457,8 +511,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   P.eval_range = p->eval_range; P.bp_resl = p->bp_resl;
   P.inv_step = 1.0 / p->step; P.off_magic = 20.0 / p->step - 0.5 + 6755399441055744.0;
   P.pos = c->d_pos; P.chr_start = c->d_chr_start; P.chr_nsnps = c->d_chr_nsnps;
-  P.coefC = c->d_coefC; P.row_doubles = (K + 2) * 4; P.tile_lo = c->d_tile_lo; P.tile_hi = c->d_tile_hi; P.logT = c->d_logT; P.null_tab = c->d_null;
-  launch_bucket(c->n, c->n_pad, c->d_cls0, 0, c->d_pos, c->d_null, c->d_tkey0, c->d_tpos0, c->d_tnull0, 1, c->stream);
+  P.coefC = c->d_coefC; P.row_doubles = (K + 2) * 4; P.tile_lo = c->d_tile_lo; P.tile_hi = c->d_tile_hi; P.logT = c->d_logT; P.null_tab = c->d_null; P.pmax = c->d_pmax;
+  launch_bucket(c->n, c->n_pad, c->d_cls0, 0, c->d_pos, c->d_null, c->ts0, 1, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
@@ -471,8 +525,8 @@ extern "C" void fscl_destroy(void *ctx) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_pos); cudaFree(c->d_cls0); cudaFree(c->d_chr_start); cudaFree(c->d_chr_nsnps);
-  cudaFree(c->d_coefC); cudaFree(c->d_tkey0); cudaFree(c->d_tpos0); cudaFree(c->d_tnull0); cudaFree(c->d_tnull);
-  cudaFree(c->d_tile_lo); cudaFree(c->d_tile_hi); cudaFree(c->d_tkey); cudaFree(c->d_tpos); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
+  cudaFree(c->d_coefC); free_tiles(c->ts0); free_tiles(c->ts); cudaFree(c->d_pmax);
+  cudaFree(c->d_tile_lo); cudaFree(c->d_tile_hi); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
   cudaFree(c->d_pcls); cudaFree(c->d_scratch); cudaFree(c->d_blocks); cudaFree(c->d_blkoff);
   cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_matrix);
   cudaFree(c->d_blkcnt); cudaFree(c->d_chr_end); cudaFree(c->d_active[0]); cudaFree(c->d_active[1]);
@@ -571,7 +625,7 @@ static int apply_blocks(Ctx *c, int n_slots) {
   launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, n_slots, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
-  launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull,
+  launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->ts,
                 n_slots, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -755,7 +809,7 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
     launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, ns, c->stream);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->d_tkey, c->d_tpos, c->d_tnull, ns,
+    launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->ts, ns,
                   c->stream);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
@@ -767,7 +821,7 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
     CK(cudaGetLastError());
     cudaEvent_t e2 = c->ev2, e3 = c->ev3;
     CK(cudaEventRecord(e2, c->stream));
-    launch_scan(c->P, c->d_tasks, c->d_out, c->d_tkey, c->d_tpos, c->d_tnull, (int)((size_t)ns * na), 0, c->d_terms, dm,
+    launch_scan(c->P, c->d_tasks, c->d_out, c->ts, (int)((size_t)ns * na), c->no_prune ? kFlagNoPrune : 0, c->d_terms, dm,
                 c->stream);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
@@ -1216,15 +1270,29 @@ extern "C" int fscl_project_pvalues(int n_pts, const fscl_pt_t *pts, const float
 }
 
 // --------------------------------------------------------------------------- bench / stats
+extern "C" int fscl_set_exact_candidates(void *ctx, int on) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "null context");
+  c->no_prune = on != 0;
+  return FSCL_OK;
+}
+
 extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !s) return fail(FSCL_ERR_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  unsigned long long redo = 0;
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(&redo, c->d_terms + 1, sizeof redo, cudaMemcpyDeviceToHost));
+  c->stats.bound_failures = (int32_t)std::min<unsigned long long>(redo, 0x7FFFFFFFull);
   *s = c->stats;
   return FSCL_OK;
 }
 extern "C" int fscl_reset_stats(void *ctx) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  cudaSetDevice(c->device);
+  cudaMemsetAsync(c->d_terms + 1, 0, sizeof(unsigned long long), c->stream);
   memset(&c->stats, 0, sizeof c->stats);
   return FSCL_OK;
 }

@@ -16,6 +16,8 @@ __device__ __forceinline__ double dev_logt(const double *__restrict__ T, int d) 
   return sh ? c + t : t;
 }
 
+constexpr int kMaxTilesC = (2 * 81920 + 1) / kTile + 3;   // tiles a window can touch (eval_range <= 81920)
+
 struct PtS {          // one evaluated scan point, shared by the CTA
   int nearest, sweep_pos, wstart, wend, dnear;
   double lalpha, clr;
@@ -150,11 +152,30 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
 // sm-search.c:281; CLR is exactly 0 in flat regions).  That is reproduced by
 // returning S[j] = (N + sum_j) - N with N the window null sum, which the coarse
 // pass (WITHN) accumulates alongside.
+//
+// Pruning by bounds (use_bound, coarse pass only).  A candidate can only matter if it is the
+// strict maximum (sm-search.c:281), so a candidate whose sum is provably below an exactly
+// evaluated one needs no exact value.  For a tile that lies wholly inside the window, on one side
+// of the sweep and wholly inside the cuts of the first jfull <= 4 candidates, the tile's share of
+// those sums is bounded from above by  sum over class runs  count * max_{knots the tile spans}
+// pmax[class][knot]  (pmax = upper bound of the spline piece minus null over its knot interval,
+// host-built), about 100 run visits instead of 2048 site visits per candidate.  The caller
+// checks  bound + tolerance < best exact candidate  and otherwise repeats the pass exactly.
+struct PhaseScratch {
+  int tile[kMaxTilesC];                 // per-tile classification
+  int list[kMaxTilesC];                 // tiles that need a per-site walk, in order
+  double tn[kMaxTilesC];                // per-tile null sums (WITHN)
+  unsigned short kr[kMaxTilesC][4];     // bounded tiles: first knot | extra knots << 8 per candidate
+  int n_list, bmask;
+};
+
 template <int NA, bool COUNT, bool WITHN>
 __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ tkey,
                                           const int *__restrict__ tpos, const double *__restrict__ tnull,
-                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S, int *s_tile,
-                                          unsigned long long &nterms) {
+                                          const int *__restrict__ trun, const int *__restrict__ tnrun,
+                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
+                                          PhaseScratch &W, bool use_bound, unsigned long long &nterms) {
+  int *s_tile = W.tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na_all = c_alpha.n[row];
   int na = 0;                       // alphas whose cut admits the nearest site (prefix: dmax descends)
@@ -163,8 +184,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (j < na_all && R.dnear <= c_alpha.dmax[row][j]) na = j + 1;
   double acc[NA];
   double accn = 0.0;
+  double ub[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < NA; j++) acc[j] = 0.0;
+  if (threadIdx.x == 0) W.bmask = 0;
   if (na > 0 || WITHN) {
     const int sweep = R.sweep_pos, ws = R.wstart, we = R.wend;
     const unsigned wlen = (unsigned)(we - ws);
@@ -175,7 +198,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const double inv_step = P.inv_step, offm = P.off_magic;
     const int t0 = ws / kTile, t1 = we / kTile;
     // ---- classify the tiles of the window once per pass, one thread per tile (shared table) ----
-    // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19
+    // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19 | bounded << 20
+    __syncthreads();                      // W.bmask reset above; the previous pass is done with W
     for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
       const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
       const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
@@ -191,19 +215,77 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       if (!ins) jf = 0;
       // which branch of logt (sm-search.c:40-46) the whole tile takes: 2 = >>16, 1 = >>8, 0 = mixed
       const int lu = (ins && dnr > 0xFFFFFF) ? 2 : ((ins && dnr > 0xFFFF && dfar <= 0xFFFFFF) ? 1 : 0);
-      const int needed = WITHN || ja > 0;
-      s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19);
+      // a per-site walk is needed for the sites a cut or the window edge selects, and for the null
+      // sum of a tile the window cuts; complete tiles take their null sum from tnull
+      int needed = (WITHN && !ins) || ja > 0;
+      int bounded = 0;
+      if (WITHN) {
+        if (ins) W.tn[t - t0] = __ldg(tnull + t);
+        if (use_bound && ins && dnr > 0 && jf >= 1 && jf <= 4) {
+          // knots the tile spans per bounded candidate (logt and the knot map are monotone)
+          const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
+          bounded = 1;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const double la = c_alpha.la[row][j];
+            const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), (int)kclamp);
+            const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), (int)kclamp);
+            if (j < jf && kb - ka > 3) bounded = 0;
+            W.kr[t - t0][j] = (unsigned short)(ka | (min(max(kb - ka, 0), 3) << 8));
+          }
+          if (bounded) {
+            atomicOr(&W.bmask, (1 << jf) - 1);
+            needed = ja > jf;                 // only a cut crossing the tile is left for the walk
+          }
+        }
+      }
+      s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (bounded << 20);
     }
     __syncthreads();
-    // tiles that can hold an admitted site: [ta, tb] (every tile when the null sum is wanted)
-    int ta = t0, tb = t1;
-    if (!WITHN) {
-      ta = 0x7FFFFFFF; tb = -1;
+    // tiles that need the per-site walk, in order
+    if (warp == 0) {
+      int cnt = 0;
       for (int b0 = t0; b0 <= t1; b0 += 32) {
         const int t = b0 + lane;
-        const bool hit = t <= t1 && (s_tile[t - t0] >> 19);
+        const bool hit = t <= t1 && ((s_tile[t - t0] >> 19) & 1);
         const unsigned m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (m) { ta = min(ta, b0 + __ffs(m) - 1); tb = max(tb, b0 + 31 - __clz(m)); }
+        if (hit) W.list[cnt + __popc(m & ((1u << lane) - 1u))] = t;
+        cnt += __popc(m);
+      }
+      if (lane == 0) W.n_list = cnt;
+    }
+    __syncthreads();
+    const int n_tl = W.n_list;
+    // window null sum from the complete tiles, in tile order (the cut tiles add their sites below)
+    if (WITHN && threadIdx.x == 0)
+      for (int t = t0; t <= t1; t++)
+        if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
+    // ---- bounded tiles: one warp per tile, lanes over its class runs ----
+    if (WITHN && W.bmask) {
+      const double *__restrict__ pm = P.pmax;
+      const unsigned prow = (unsigned)P.n_knots + 2u;
+      for (int t = t0 + warp; t <= t1; t += kScanWarps) {
+        const int info = s_tile[t - t0];
+        if (!((info >> 20) & 1)) continue;
+        const int jf = (info >> 8) & 0xFF;
+        const int nr = __ldg(tnrun + t);
+        const int *__restrict__ rl = trun + (size_t)t * kTile;
+        unsigned short kr[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) kr[j] = W.kr[t - t0][j];
+        for (int r = lane; r < nr; r += 32) {
+          const unsigned e = (unsigned)__ldg(rl + r);
+          const double cntd = (double)(e >> 20);
+          const double *__restrict__ pr = pm + (size_t)(e & 0xFFFFFu) * prow;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if (j >= jf) break;
+            const int ka = kr[j] & 0xFF, ex = kr[j] >> 8;
+            double m = __ldg(pr + ka);
+            for (int q = 1; q <= ex; q++) m = fmax(m, __ldg(pr + ka + q));   // fmax drops a NaN: NaN tables are kept out on the host (pmax = +inf)
+            ub[j] = fma(cntd, m, ub[j]);
+          }
+        }
       }
     }
     // A warp owns chunks {warp, warp+8, ...} of every tile and walks them in batches of kB:
@@ -213,23 +295,23 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     constexpr int kB = FSCL_KB < CH ? FSCL_KB : CH;
     constexpr int HB = CH / kB;                       // batches per tile
     static_assert(CH % kB == 0, "tile must split into whole batches");
-    const int n_batches = tb >= ta ? (tb - ta + 1) * HB : 0;
+    const int n_batches = n_tl * HB;
     const int woff = warp * 32 + lane;
-    auto batch_base = [&](int h) { return (ta + h / HB) * kTile + (h % HB) * (kB * kScanWarps * 32) + woff; };
+    auto batch_base = [&](int h) { return W.list[h / HB] * kTile + (h % HB) * (kB * kScanWarps * 32) + woff; };
     int nkey[kB], npos[kB];
     if (n_batches > 0) {
       const int i = batch_base(0);
 #pragma unroll
       for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
     }
-    int jany = 0, jfull = 0, lut = 0;
+    int jany = 0, jfull = 0, lut = 0, jskip = 0;
     bool inside = false;
     for (int h = 0; h < n_batches; h++) {
-      const int t = ta + h / HB;
+      const int t = W.list[h / HB];
       if (h % HB == 0) {
         const int info = s_tile[t - t0];
         jany = info & 0xFF; jfull = (info >> 8) & 0xFF; inside = (info >> 16) & 1; lut = (info >> 17) & 3;
-        if (WITHN && inside && threadIdx.x == 0) accn += __ldg(tnull + t);
+        jskip = ((info >> 20) & 1) ? jfull : 0;     // bounded tile: its first jfull candidates are not walked
       }
       int key[kB], d[kB];
       double x0[kB];
@@ -270,7 +352,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         }
       }
       // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots)
-      if (jfull > 0 && jfull <= 4) {
+      if (jfull > 0 && jfull <= 4 && jskip == 0) {
         // far tiles: at most four alphas, rows double-buffered across the records of the batch
         if (jfull == 4) batch_terms_pipelined<4, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
         else if (jfull == 3) batch_terms_pipelined<3, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
@@ -326,6 +408,14 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) accn += __shfl_xor_sync(0xFFFFFFFFu, accn, o);
     if (lane == 0) red[warp][kMaxFine] = accn;
+    static_assert(NA + 4 <= kMaxFine || !WITHN, "bound sums share the reduction buffer with the candidates");
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      double v = ub[j];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+      if (lane == 0) red[warp][NA + j] = v;
+    }
   }
   __syncthreads();
   if (threadIdx.x < NA) {
@@ -338,14 +428,22 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
-    S[threadIdx.x] = (int)threadIdx.x < na ? (N + v) - N : 0.0;
+    double s = (int)threadIdx.x < na ? (N + v) - N : 0.0;
+    if (WITHN && threadIdx.x < 4 && ((W.bmask >> threadIdx.x) & 1)) {
+      // bounded candidate: exact share of the walked tiles + bound of the others + tolerance for the
+      // rounding of both (the terms are O(1e2), a window has < 2e5 of them)
+      double b = 0.0;
+#pragma unroll
+      for (int w = 0; w < kScanWarps; w++) b += red[w][NA + threadIdx.x];
+      s = (v + b) + (1e-4 + 1e-9 * (fabs(v) + fabs(b)));
+    }
+    S[threadIdx.x] = s;
     if (WITHN && threadIdx.x == 0) S[kMaxFine] = N;
   }
   __syncthreads();
   if (WITHN && threadIdx.x == 0) R.nsum = S[kMaxFine];
 }
 
-constexpr int kMaxTiles = (2 * 81920 + 1) / kTile + 3;   // tiles a window can touch (eval_range <= 81920)
 
 // search_maxpos scan-chromosome.c:103-139: one CTA per (permutation slot, cell).
 // One copy of the evaluation code serves the two end points and every
@@ -354,17 +452,21 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks)
 scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tasks, OutPt *__restrict__ out,
                   const int *__restrict__ tkey_all, const int *__restrict__ tpos_all,
-                  const double *__restrict__ tnull_all, int flags, unsigned long long *term_counter,
+                  const double *__restrict__ tnull_all, const int *__restrict__ trun_all,
+                  const int *__restrict__ tnrun_all, int flags, unsigned long long *term_counter,
                   double *__restrict__ clr_matrix) {
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
-  __shared__ int s_row, s_next;
-  __shared__ int s_tile[kMaxTiles];
+  __shared__ int s_row, s_next, s_redo;
+  __shared__ PhaseScratch W;
   const Task t = tasks[blockIdx.x];
   const int *__restrict__ tkey = tkey_all + (size_t)t.slot * P.n_pad;
   const int *__restrict__ tpos = tpos_all + (size_t)t.slot * P.n_pad;
   const double *__restrict__ tnull = tnull_all + (size_t)t.slot * (P.n_pad / kTile);
+  const int *__restrict__ trun = trun_all + (size_t)t.slot * P.n_pad;
+  const int *__restrict__ tnrun = tnrun_all + (size_t)t.slot * (P.n_pad / kTile);
+  const bool prune = !(flags & kFlagNoPrune);
   unsigned long long nterms = 0;
 
   int pos = t.start_pos;
@@ -372,19 +474,30 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
     if (threadIdx.x == 0) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
-    dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, M, kCoarse, red, S, s_tile, nterms);
-    if (threadIdx.x == 0) {
-      // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
-      // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
-      // (scan-chromosome.c:97), whose fine interval is that of the last coarse value
-      int best = -1; double bs = -1.7976931348623157e308;
-      for (int j = 0; j < kCoarse; j++) if (S[j] > bs) { bs = S[j]; best = j; }
-      M.clr = bs; M.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
-      s_row = best < 0 ? kCoarse - 1 : best;
+    for (int exact = prune ? 0 : 1; exact < 2; exact++) {
+      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, M, kCoarse, red, S, W, exact == 0, nterms);
+      if (threadIdx.x == 0) {
+        // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
+        // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
+        // (scan-chromosome.c:97), whose fine interval is that of the last coarse value.
+        // Bounded candidates (W.bmask) carry an upper bound: they are out of the race when it is
+        // below the best exact candidate (a tie would go to the lower index, hence strictly below);
+        // otherwise the pass is repeated without bounds.
+        const int bm = W.bmask;
+        int best = -1; double bs = -1.7976931348623157e308;
+        for (int j = 0; j < kCoarse; j++) if (!((bm >> j) & 1) && S[j] > bs) { bs = S[j]; best = j; }
+        int redo = 0;
+        for (int j = 0; j < 4; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
+        s_redo = redo;
+        if (redo) atomicAdd(term_counter + 1, 1ull);
+        M.clr = bs; M.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
+        s_row = best < 0 ? kCoarse - 1 : best;
+      }
+      __syncthreads();
+      if (!s_redo) break;
     }
-    __syncthreads();
     const int row = s_row;
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, M, row, red, S, s_tile, nterms);
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, M, row, red, S, W, false, nterms);
     if (threadIdx.x == 0) {
       double bs = M.clr, la = M.lalpha;
       const int nf = c_alpha.n[row];
@@ -423,13 +536,13 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   }
 }
 
-void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *tkey_all, const int *tpos_all,
-                 const double *tnull_all, int n_tasks, int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
+                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
   if (n_tasks <= 0) return;
   if (flags & kFlagCount)
-    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, tkey_all, tpos_all, tnull_all, flags, term_counter, clr_matrix);
+    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, flags, term_counter, clr_matrix);
   else
-    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, tkey_all, tpos_all, tnull_all, flags, term_counter, clr_matrix);
+    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, flags, term_counter, clr_matrix);
 }
 
 // ---------------------------------------------------------------------------
@@ -478,9 +591,12 @@ constexpr int kBucketThreads = kTile / 2 < 1024 ? kTile / 2 : 1024;
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stride,
               const int *__restrict__ pos, const double *__restrict__ null_tab, int *__restrict__ tkey_all,
-              int *__restrict__ tpos_all, double *__restrict__ tnull_all) {
+              int *__restrict__ tpos_all, double *__restrict__ tnull_all, int *__restrict__ trun_all,
+              int *__restrict__ tnrun_all) {
   __shared__ unsigned keys[kTile];
   __shared__ double wsum[kBucketThreads / 32];
+  __shared__ int hpos[kTile + 1];
+  __shared__ int cbase[kTile / 32 + 1];
   const int tile = blockIdx.x, slot = blockIdx.y;
   const int *cls = cls_all + (size_t)slot * cls_stride;
   const int base = tile * kTile;
@@ -506,6 +622,35 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
     tkey[base + e] = (int)((kk >> 12) | ((unsigned)lidx << 20));
     tpos[base + e] = gi < n ? __ldg(pos + gi) : 0;
   }
+  // run list of the sorted tile: one entry class | count << 20 per run of equal classes (the far-tile
+  // bounds of scan_cells_kernel walk runs, not sites)
+  {
+    const int lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
+      const bool head = e == 0 || (keys[e] >> 12) != (keys[e - 1] >> 12);
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+      if (lane == 0) cbase[e >> 5] = __popc(m);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int acc = 0;
+      for (int q = 0; q < kTile / 32; q++) { const int v = cbase[q]; cbase[q] = acc; acc += v; }
+      cbase[kTile / 32] = acc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
+      const bool head = e == 0 || (keys[e] >> 12) != (keys[e - 1] >> 12);
+      const unsigned m = __ballot_sync(0xFFFFFFFFu, head);
+      if (head) hpos[cbase[e >> 5] + __popc(m & ((1u << lane) - 1u))] = e;
+    }
+    const int nrun = cbase[kTile / 32];
+    if (threadIdx.x == 0) hpos[nrun] = kTile;
+    __syncthreads();
+    int *trun = trun_all + (size_t)slot * n_pad + base;
+    for (int r = threadIdx.x; r < nrun; r += kBucketThreads)
+      trun[r] = (int)((keys[hpos[r]] >> 12) | ((unsigned)(hpos[r + 1] - hpos[r]) << 20));
+    if (threadIdx.x == 0) tnrun_all[(size_t)slot * (n_pad / kTile) + tile] = nrun;
+  }
   // null log-likelihood of the tile (fixed tree; only complete tiles are ever read)
   double v = 0.0;
   for (int e = threadIdx.x; e < kTile; e += kBucketThreads)
@@ -522,12 +667,11 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
 }
 
 void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
-                   const double *null_tab, int *tkey_all, int *tpos_all, double *tnull_all, int n_slots,
-                   cudaStream_t s) {
+                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s) {
   if (n_slots <= 0) return;
   dim3 grid(n_pad / kTile, n_slots);
-  bucket_kernel<<<grid, kBucketThreads, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, tkey_all, tpos_all,
-                                          tnull_all);
+  bucket_kernel<<<grid, kBucketThreads, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, ts.key, ts.pos,
+                                          ts.tnull, ts.run, ts.nrun);
 }
 
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,

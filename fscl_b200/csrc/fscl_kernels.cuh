@@ -50,6 +50,15 @@ struct Params {
   const int *tile_lo, *tile_hi;    // [n_pad / kTile] smallest / largest position inside each tile
   const double *logT;              // [65536]
   const double *null_tab;          // [n_cls]
+  const double *pmax;              // [n_cls][n_knots+2] upper bound of (spline piece - null) over its knot interval
+};
+
+// One genome instance (observed, or the permutation slots) as class-bucketed tiles.
+struct TileSet {
+  int *key, *pos;                  // [slots][n_pad]  class | index_in_tile << 20 ; position
+  double *tnull;                   // [slots][n_pad / kTile]  null log-likelihood of the tile
+  int *run;                        // [slots][n_pad]  per tile: class | count << 20 for every run of equal classes
+  int *nrun;                       // [slots][n_pad / kTile]  runs in the tile
 };
 
 struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix
@@ -69,11 +78,10 @@ struct AlphaTables {
 
 void upload_alpha_tables(const AlphaTables &t);
 
-void launch_scan(const Params &P, const Task *tasks, OutPt *out, const int *tkey_all, const int *tpos_all,
-                 const double *tnull_all, int n_tasks, int flags, unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
+void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
+                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
 void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
-                   const double *null_tab, int *tkey_all, int *tpos_all, double *tnull_all, int n_slots,
-                   cudaStream_t s);
+                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s);
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
                     const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s);
 void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,
@@ -89,6 +97,7 @@ void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);
 
 enum { kFlagSingle = 1,      // evaluate start_pos only (search_maxalpha at a point)
        kFlagNullSum = 2,     // also sum null_tab over the final window
-       kFlagCount = 4 };     // count SNP-terms (roofline numerator)
+       kFlagCount = 4,       // count the SNP-terms the kernel evaluates (roofline numerator)
+       kFlagNoPrune = 8 };   // evaluate every candidate of the coarse list exactly (no pruning by bounds)
 
 }  // namespace fscl

@@ -88,7 +88,8 @@ typedef struct {
   int64_t n_rounds;
   int64_t n_blocks;         /* permutation blocks applied                  */
   int32_t d7_hits;          /* blocks that overshot the array end (defined behaviour) */
-  int32_t reserved;
+  int32_t bound_failures;   /* coarse passes repeated exactly because a bounded candidate could not be excluded
+                               (filled by fscl_get_stats; counted since fscl_create / fscl_reset_stats) */
   double score_kernel_ms;   /* CUDA-event time of the scan kernel, summed  */
   double permute_kernel_ms; /* CUDA-event time of the block-permute kernel */
   int64_t score_launches, permute_launches;
@@ -169,6 +170,11 @@ int fscl_ncx2_sf(int n, const double *x, double df, const double *lambda, double
 /* device-resident variants used by bench.py: time whole scans with inputs in HBM */
 int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_terms,
                     int64_t *terms_out, fscl_stats_t *stats);
+/* search_maxalpha's coarse list (sm-search.c:276-282): by default a candidate whose sum is provably
+ * below an exactly evaluated one (upper bound from per-tile class counts) is not
+ * evaluated site by site -- the selected alpha, CLR and every later decision are unchanged.
+ * on = 1 evaluates every candidate exactly (A/B tests, reference-equivalent term counts). */
+int fscl_set_exact_candidates(void *ctx, int on);
 int fscl_get_stats(void *ctx, fscl_stats_t *stats);
 int fscl_reset_stats(void *ctx);
 /* FP64 FMA peak of the device (dependent-chain microbenchmark), in TFLOP/s */

@@ -94,3 +94,70 @@ def test_genome_shapes_match_oracle(api, shape):
     g2, st, _ = sc.scan_permute(got, n_perm, G, rng=api.RNG_PHILOX, seed=31)
     assert np.array_equal(g2["permute_p"], w2["permute_p"]) and np.array_equal(g2["permute_n"], w2["permute_n"])
     assert np.array_equal(g2["permute_finished"], w2["finished"]) and st["n_scored"] == scored
+
+
+def _same_points(a, b):
+    return a.tobytes() == b.tobytes()
+
+
+def test_c2_candidate_pruning_changes_nothing(api, c2):
+    """Pruning dominated coarse candidates by their upper bounds must leave every
+    output bit unchanged: forward scan, permuted scans, counts; and it must actually prune."""
+    flat, sc, G = c2
+    try:
+        sc.set_exact_candidates(True)
+        a = sc.scan_chromosome(G)
+        terms_exact, _ = sc.bench_scan(G, 0, count_terms=True)
+        pa, _, _ = sc.scan_permute(a, 5, G, rng=api.RNG_PHILOX, seed=77, prune=0)
+        sc.set_exact_candidates(False)
+        sc.reset_stats()
+        b = sc.scan_chromosome(G)
+        failures = sc.stats()["bound_failures"]
+        terms_pruned, _ = sc.bench_scan(G, 0, count_terms=True)
+        pb, _, _ = sc.scan_permute(b, 5, G, rng=api.RNG_PHILOX, seed=77, prune=0)
+    finally:
+        sc.set_exact_candidates(False)
+    assert _same_points(a, b) and _same_points(pa, pb)
+    assert 0 < terms_pruned < 0.5 * terms_exact          # the far tiles of the three widest candidates dominate c2
+    # at the planted sweep a bounded candidate wins, so the exact pass has to run there -- and only there
+    assert 0 < failures < 0.05 * 12 * len(b)
+
+
+@pytest.mark.parametrize("shape", ["mid100", "c4", "c5", "sweep"])
+def test_candidate_pruning_changes_nothing_on_other_shapes(api, shape):
+    if shape == "mid100":
+        tab, opt = synth.config2(scale=0.1)
+        G = opt["G"]
+    elif shape == "c4":
+        tab, opt = synth.config4(scale=0.02)
+        G = opt["G"]
+    elif shape == "c5":
+        tab, opt = synth.config5(scale=0.004)
+        G = opt["G"] * 4
+    else:
+        # a sweep footprint tens of Mb wide: wide (low-alpha) candidates score high, so the bounds
+        # cannot exclude them everywhere and the exact pass has to run
+        tab, opt = synth.config2(scale=0.5, planted=False)
+        rng = np.random.default_rng(3)
+        mid = int(tab["pos"][len(tab["pos"]) // 2])
+        hit = (np.abs(tab["pos"] - mid) < 12_000_000) & (rng.random(len(tab["count"])) < 0.7)
+        tab["count"][hit] = np.where(rng.random(int(hit.sum())) < 0.5, rng.integers(1, 3, int(hit.sum())),
+                                     rng.integers(97, 100, int(hit.sum())))
+        G = opt["G"]
+    flat = po.RefProblem(tab).flatten()
+    sc = api.Scanner(flat)
+    sc.set_exact_candidates(True)
+    a = sc.scan_chromosome(G)
+    pa, _, _ = sc.scan_permute(a, 3, G, rng=api.RNG_PHILOX, seed=5, prune=0)
+    sc.set_exact_candidates(False)
+    sc.reset_stats()
+    b = sc.scan_chromosome(G)
+    failures = sc.stats()["bound_failures"]
+    pb, _, _ = sc.scan_permute(b, 3, G, rng=api.RNG_PHILOX, seed=5, prune=0)
+    assert _same_points(a, b) and _same_points(pa, pb)
+    if shape == "sweep":
+        assert failures > 0                               # bounds that could not exclude their candidate
+        o = po.Oracle(flat, mode=2)
+        want, _ = o.scan(G)
+        assert np.array_equal(b["sweep_pos"], want["sweep_pos"]) and np.array_equal(b["lalpha"], want["lalpha"])
+        assert clr_close(b["clr"], want["clr"]).all()

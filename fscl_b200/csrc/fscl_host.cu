@@ -184,8 +184,8 @@ int ensure_tasks(Ctx *c, size_t n) {
 // clamp rows K, K+1 repeat piece K-1 (sm-spline.c:53) up to x = 4 and one step beyond.  End
 // points, interior critical points, plus a margin far above the rounding of a Horner evaluation.
 // A piece with a non-finite coefficient (D14) gets +inf: its candidates are never pruned.
-void build_piece_maxima(const double *coefC, int NC, int K, double step, std::vector<double> &pmax) {
-  pmax.assign((size_t)NC * (K + 2), 0.0);
+void build_piece_maxima(const double *coefC, int NC, int K, double step, std::vector<double> &ptab) {
+  std::vector<double> pmax((size_t)NC * (K + 2), 0.0);
   for (int cl = 0; cl < NC; cl++)
     for (int k = 0; k < K + 2; k++) {
       const double *q = coefC + ((size_t)cl * (K + 2) + k) * 4;
@@ -217,6 +217,17 @@ void build_piece_maxima(const double *coefC, int NC, int K, double step, std::ve
       const double mag = std::fabs(c3) + xm * (std::fabs(c2) + xm * (std::fabs(c1) + xm * std::fabs(c0)));
       out = m + 1e-11 * mag + 1e-300;
     }
+  // sparse table for range maxima over knots, [level][knot][class]; windows are clipped at the last row
+  const size_t lv = (size_t)(K + 2) * NC;
+  ptab.assign(4 * lv, 0.0);
+  for (int k = 0; k < K + 2; k++)
+    for (int cl = 0; cl < NC; cl++) ptab[(size_t)k * NC + cl] = pmax[(size_t)cl * (K + 2) + k];
+  for (int l = 1; l < 4; l++)
+    for (int k = 0; k < K + 2; k++) {
+      const int k2 = std::min(k + (1 << (l - 1)), K + 1);
+      for (int cl = 0; cl < NC; cl++)
+        ptab[l * lv + (size_t)k * NC + cl] = std::max(ptab[(l - 1) * lv + (size_t)k * NC + cl], ptab[(l - 1) * lv + (size_t)k2 * NC + cl]);
+    }
 }
 
 void free_tiles(TileSet &t) {
@@ -244,6 +255,7 @@ int ensure_slots(Ctx *c, int slots) {
   c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
   { int rc = alloc_tiles(c->ts, slots, c->n_pad); if (rc) return rc; }
   CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
+  c->ts.cls = c->d_pcls; c->ts.cls_stride = (size_t)c->n;
   CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
   CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
   CK(cudaMalloc(&c->d_blkcnt, (size_t)(slots + 1) * sizeof(int)));
@@ -484,6 +496,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMalloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
   CK(cudaMalloc(&c->d_coefC, sizeof(double) * coefC.size()));
   { int rc = alloc_tiles(c->ts0, 1, c->n_pad); if (rc) return rc; }
+  c->ts0.cls = c->d_cls0; c->ts0.cls_stride = 0;
   CK(cudaMalloc(&c->d_pmax, sizeof(double) * pmax.size()));
   CK(cudaMemcpy(c->d_pmax, pmax.data(), sizeof(double) * pmax.size(), cudaMemcpyHostToDevice));
   CK(cudaMalloc(&c->d_tile_lo, sizeof(int) * n_tiles));

@@ -173,7 +173,7 @@ template <int NA, bool COUNT, bool WITHN>
 __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ tkey,
                                           const int *__restrict__ tpos, const double *__restrict__ tnull,
                                           const int *__restrict__ trun, const int *__restrict__ tnrun,
-                                          PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
+                                          const int *__restrict__ icls, PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
                                           PhaseScratch &W, bool use_bound, unsigned long long &nterms) {
   int *s_tile = W.tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -197,8 +197,42 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const unsigned kclamp = (unsigned)P.n_knots + 1u;
     const double inv_step = P.inv_step, offm = P.off_magic;
     const int t0 = ws / kTile, t1 = we / kTile;
+    // ---- candidates with a narrow cut are summed straight from the position-ordered arrays ----
+    // Every window site outside [iL, iR] (kDirect sites either side of the nearest one) is beyond
+    // the cut of the candidates j >= jd, so those never enter the tile walk: in a class-sorted tile
+    // their few admitted sites would cost a visit of all 2048.
+    const int iL = max(ws, R.nearest - kDirect), iR = min(we, R.nearest + kDirect);
+    int jd = na;
+    {
+      const int gl = iL == ws ? 0x7FFFFFFF : sweep - __ldg(P.pos + iL), gr = iR == we ? 0x7FFFFFFF : __ldg(P.pos + iR) - sweep;
+      const int g = min(gl, gr);
+#pragma unroll
+      for (int j = NA - 1; j >= 0; j--)
+        if (j < na && c_alpha.dmax[row][j] < g) jd = j;
+    }
+    const int naw = jd;                 // candidates the tile walk (or a bound) accounts for
+    if (jd < na) {
+      for (int i = iL + (int)threadIdx.x; i <= iR; i += kScanThreads) {
+        const int dd = __ldg(P.pos + i) - sweep, d = dd < 0 ? -dd : dd;
+        const double x0 = dev_logt(T, d);
+        const char *cr = coef + (size_t)__ldg(icls + i) * rowbytes;
+#pragma unroll
+        for (int j = 0; j < NA; j++) {
+          if (j < jd) continue;
+          if (j >= na) break;
+          if (d <= c_alpha.dmax[row][j]) {
+            const double x = x0 + c_alpha.la[row][j];
+            const unsigned k = min((unsigned)max(__double2loint(fma(x, inv_step, offm)), 0), kclamp);
+            double c0, c1, c2, c3;
+            ld_row(reinterpret_cast<const double *>(cr + (unsigned long long)k * 32ull), c0, c1, c2, c3);
+            acc[j] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
+            if (COUNT) nterms += 1ull;
+          }
+        }
+      }
+    }
     // ---- classify the tiles of the window once per pass, one thread per tile (shared table) ----
-    // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19 | bounded << 20
+    // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19 | jb << 20  (jb = leading candidates bounded)
     __syncthreads();                      // W.bmask reset above; the previous pass is done with W
     for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
       const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
@@ -209,8 +243,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       int ja = 0, jf = 0;
 #pragma unroll
       for (int j = 0; j < NA; j++) {
-        if (j < na && c_alpha.dmax[row][j] >= dnr) ja = j + 1;
-        if (j < na && c_alpha.dmax[row][j] >= dfar) jf = j + 1;
+        if (j < naw && c_alpha.dmax[row][j] >= dnr) ja = j + 1;
+        if (j < naw && c_alpha.dmax[row][j] >= dfar) jf = j + 1;
       }
       if (!ins) jf = 0;
       // which branch of logt (sm-search.c:40-46) the whole tile takes: 2 = >>16, 1 = >>8, 0 = mixed
@@ -218,28 +252,32 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       // a per-site walk is needed for the sites a cut or the window edge selects, and for the null
       // sum of a tile the window cuts; complete tiles take their null sum from tnull
       int needed = (WITHN && !ins) || ja > 0;
-      int bounded = 0;
+      int jb = 0;
       if (WITHN) {
         if (ins) W.tn[t - t0] = __ldg(tnull + t);
-        if (use_bound && ins && dnr > 0 && jf >= 1 && jf <= 4) {
-          // knots the tile spans per bounded candidate (logt and the knot map are monotone)
+        if (use_bound && ins && dnr > 0 && jf >= 1) {
+          // knots the tile spans per candidate (logt and the knot map are monotone).  The bounded
+          // candidates are a prefix: up to 8 knots wide for a candidate whose cut lies well beyond
+          // the tile (far from competitive), 4 for the last one that still covers the tile.
           const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
-          bounded = 1;
+          bool open = true;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             const double la = c_alpha.la[row][j];
             const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), (int)kclamp);
             const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), (int)kclamp);
-            if (j < jf && kb - ka > 3) bounded = 0;
-            W.kr[t - t0][j] = (unsigned short)(ka | (min(max(kb - ka, 0), 3) << 8));
+            const int ex = max(kb - ka, 0);
+            open = open && j < jf && ex <= (j == jf - 1 ? 3 : 7);
+            if (open) jb = j + 1;
+            W.kr[t - t0][j] = (unsigned short)(ka | (min(ex, 7) << 8));
           }
-          if (bounded) {
-            atomicOr(&W.bmask, (1 << jf) - 1);
-            needed = ja > jf;                 // only a cut crossing the tile is left for the walk
+          if (jb) {
+            atomicOr(&W.bmask, (1 << jb) - 1);
+            needed = ja > jb;                 // candidates left for the walk
           }
         }
       }
-      s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (bounded << 20);
+      s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (jb << 20);
     }
     __syncthreads();
     // tiles that need the per-site walk, in order
@@ -261,29 +299,31 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       for (int t = t0; t <= t1; t++)
         if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
     // ---- bounded tiles: one warp per tile, lanes over its class runs ----
+    // pmax is a sparse table [level][knot][class]: level l holds the maximum over knots k .. k+2^l-1
     if (WITHN && W.bmask) {
       const double *__restrict__ pm = P.pmax;
-      const unsigned prow = (unsigned)P.n_knots + 2u;
+      const unsigned ncls = (unsigned)P.n_cls, lvl_stride = ((unsigned)P.n_knots + 2u) * ncls;
       for (int t = t0 + warp; t <= t1; t += kScanWarps) {
-        const int info = s_tile[t - t0];
-        if (!((info >> 20) & 1)) continue;
-        const int jf = (info >> 8) & 0xFF;
+        const int jb = (s_tile[t - t0] >> 20) & 7;
+        if (jb == 0) continue;
         const int nr = __ldg(tnrun + t);
         const int *__restrict__ rl = trun + (size_t)t * kTile;
-        unsigned short kr[4];
+        unsigned o1[4], o2[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) kr[j] = W.kr[t - t0][j];
+        for (int j = 0; j < 4; j++) {
+          const unsigned kr = W.kr[t - t0][j], ka = kr & 0xFF, ex = kr >> 8;
+          const unsigned lv = 31 - __clz(ex + 1);
+          o1[j] = lv * lvl_stride + ka * ncls;
+          o2[j] = lv * lvl_stride + (ka + ex + 1 - (1u << lv)) * ncls;
+        }
         for (int r = lane; r < nr; r += 32) {
-          const unsigned e = (unsigned)__ldg(rl + r);
+          const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
           const double cntd = (double)(e >> 20);
-          const double *__restrict__ pr = pm + (size_t)(e & 0xFFFFFu) * prow;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            if (j >= jf) break;
-            const int ka = kr[j] & 0xFF, ex = kr[j] >> 8;
-            double m = __ldg(pr + ka);
-            for (int q = 1; q <= ex; q++) m = fmax(m, __ldg(pr + ka + q));   // fmax drops a NaN: NaN tables are kept out on the host (pmax = +inf)
-            ub[j] = fma(cntd, m, ub[j]);
+            if (j >= jb) break;
+            // fmax drops a NaN operand: tables with NaN pieces carry +inf here (host), never pruned
+            ub[j] = fma(cntd, fmax(__ldg(pm + o1[j] + cl), __ldg(pm + o2[j] + cl)), ub[j]);
           }
         }
       }
@@ -311,7 +351,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       if (h % HB == 0) {
         const int info = s_tile[t - t0];
         jany = info & 0xFF; jfull = (info >> 8) & 0xFF; inside = (info >> 16) & 1; lut = (info >> 17) & 3;
-        jskip = ((info >> 20) & 1) ? jfull : 0;     // bounded tile: its first jfull candidates are not walked
+        jskip = (info >> 20) & 7;                   // leading candidates a bound stands for: not walked
       }
       int key[kB], d[kB];
       double x0[kB];
@@ -352,7 +392,16 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         }
       }
       // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots)
-      if (jfull > 0 && jfull <= 4 && jskip == 0) {
+      if (jskip > 0) {
+        // some leading candidates are bounded: the few that are left, one at a time
+#pragma unroll
+        for (int j = 0; j < NA; j++) {
+          if (j < jskip) continue;
+          if (j >= jfull) break;
+          batch_terms_pipelined<1, kB>(acc + j, c_alpha.la[row] + j, x0, crow, inv_step, offm);
+          if (COUNT) nterms += (unsigned long long)kB;
+        }
+      } else if (jfull > 0 && jfull <= 4) {
         // far tiles: at most four alphas, rows double-buffered across the records of the batch
         if (jfull == 4) batch_terms_pipelined<4, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
         else if (jfull == 3) batch_terms_pipelined<3, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
@@ -374,21 +423,26 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         }
         if (COUNT) nterms += (unsigned long long)(jfull * kB);
       }
-      // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate
+      // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate;
+      // the rows of the kB records of a candidate are in flight together
       if (jany > jfull) {
 #pragma unroll
-        for (int u = 0; u < kB; u++) {
+        for (int j = 0; j < NA; j++) {
+          if (j < jfull) continue;
+          if (j >= jany) break;
+          const double la = c_alpha.la[row][j];
+          const int dm = c_alpha.dmax[row][j];
+          double x[kB], c0[kB], c1[kB], c2[kB], c3[kB];
 #pragma unroll
-          for (int j = 0; j < NA; j++) {
-            if (j < jfull) continue;
-            if (j >= jany) break;
-            const bool inc = dq[u] <= c_alpha.dmax[row][j];
-            const double x = x0[u] + c_alpha.la[row][j];
-            unsigned k = (unsigned)max(__double2loint(fma(x, inv_step, offm)), 0);
-            k = min(k, kclamp);
-            double c0, c1, c2, c3;
-            ld_row(reinterpret_cast<const double *>(crow[u] + (unsigned long long)k * 32ull), c0, c1, c2, c3);
-            const double y = fma(x, fma(x, fma(x, c0, c1), c2), c3);
+          for (int u = 0; u < kB; u++) {
+            x[u] = x0[u] + la;
+            const unsigned k = min((unsigned)max(__double2loint(fma(x[u], inv_step, offm)), 0), kclamp);
+            ld_row(reinterpret_cast<const double *>(crow[u] + (unsigned long long)k * 32ull), c0[u], c1[u], c2[u], c3[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < kB; u++) {
+            const double y = fma(x[u], fma(x[u], fma(x[u], c0[u], c1[u]), c2[u]), c3[u]);
+            const bool inc = dq[u] <= dm;
             if (inc) acc[j] += y;
             if (COUNT) nterms += inc ? 1ull : 0ull;
           }
@@ -453,8 +507,8 @@ __global__ void __launch_bounds__(kScanThreads, kScanMinBlocks)
 scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tasks, OutPt *__restrict__ out,
                   const int *__restrict__ tkey_all, const int *__restrict__ tpos_all,
                   const double *__restrict__ tnull_all, const int *__restrict__ trun_all,
-                  const int *__restrict__ tnrun_all, int flags, unsigned long long *term_counter,
-                  double *__restrict__ clr_matrix) {
+                  const int *__restrict__ tnrun_all, const int *__restrict__ icls_all, size_t icls_stride,
+                  int flags, unsigned long long *term_counter, double *__restrict__ clr_matrix) {
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
@@ -466,6 +520,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   const double *__restrict__ tnull = tnull_all + (size_t)t.slot * (P.n_pad / kTile);
   const int *__restrict__ trun = trun_all + (size_t)t.slot * P.n_pad;
   const int *__restrict__ tnrun = tnrun_all + (size_t)t.slot * (P.n_pad / kTile);
+  const int *__restrict__ icls = icls_all + (size_t)t.slot * icls_stride;
   const bool prune = !(flags & kFlagNoPrune);
   unsigned long long nterms = 0;
 
@@ -475,7 +530,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     if (threadIdx.x == 0) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
     for (int exact = prune ? 0 : 1; exact < 2; exact++) {
-      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, M, kCoarse, red, S, W, exact == 0, nterms);
+      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms);
       if (threadIdx.x == 0) {
         // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
         // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
@@ -497,7 +552,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       if (!s_redo) break;
     }
     const int row = s_row;
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, M, row, red, S, W, false, nterms);
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, false, nterms);
     if (threadIdx.x == 0) {
       double bs = M.clr, la = M.lalpha;
       const int nf = c_alpha.n[row];
@@ -540,9 +595,9 @@ void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &
                  unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
   if (n_tasks <= 0) return;
   if (flags & kFlagCount)
-    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, flags, term_counter, clr_matrix);
+    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix);
   else
-    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, flags, term_counter, clr_matrix);
+    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix);
 }
 
 // ---------------------------------------------------------------------------

@@ -38,6 +38,7 @@ constexpr int kScanMinBlocks = FSCL_MINBLK;   // up to 128 registers: batch stat
 constexpr int kTile = FSCL_TILE;         // sites per class-bucketed tile (<= 4096: 12-bit index in the key)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kPermThreads = 1024;
+constexpr int kDirect = 512;     // sites either side of the nearest one that narrow-cut candidates are summed from directly
 
 struct Params {
   int n_snps, n_pad, n_chr, n_cls, n_knots, eval_range, bp_resl;
@@ -50,7 +51,8 @@ struct Params {
   const int *tile_lo, *tile_hi;    // [n_pad / kTile] smallest / largest position inside each tile
   const double *logT;              // [65536]
   const double *null_tab;          // [n_cls]
-  const double *pmax;              // [n_cls][n_knots+2] upper bound of (spline piece - null) over its knot interval
+  const double *pmax;              // [4][n_knots+2][n_cls] level l: upper bound of (spline piece - null) over the knot
+                                   // intervals k .. k+2^l-1 (sparse table for range maxima, class fastest)
 };
 
 // One genome instance (observed, or the permutation slots) as class-bucketed tiles.
@@ -59,6 +61,8 @@ struct TileSet {
   double *tnull;                   // [slots][n_pad / kTile]  null log-likelihood of the tile
   int *run;                        // [slots][n_pad]  per tile: class | count << 20 for every run of equal classes
   int *nrun;                       // [slots][n_pad / kTile]  runs in the tile
+  const int *cls;                  // classes in index order, slot s at cls + s * cls_stride (not owned)
+  size_t cls_stride;
 };
 
 struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix

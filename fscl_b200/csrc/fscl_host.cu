@@ -217,16 +217,16 @@ void build_piece_maxima(const double *coefC, int NC, int K, double step, std::ve
       const double mag = std::fabs(c3) + xm * (std::fabs(c2) + xm * (std::fabs(c1) + xm * std::fabs(c0)));
       out = m + 1e-11 * mag + 1e-300;
     }
-  // sparse table for range maxima over knots, [level][knot][class]; windows are clipped at the last row
+  // range maxima over knots k .. k+w for w = 0..7, [w][knot][class]; windows are clipped at the last row
   const size_t lv = (size_t)(K + 2) * NC;
-  ptab.assign(4 * lv, 0.0);
+  ptab.assign(8 * lv, 0.0);
   for (int k = 0; k < K + 2; k++)
     for (int cl = 0; cl < NC; cl++) ptab[(size_t)k * NC + cl] = pmax[(size_t)cl * (K + 2) + k];
-  for (int l = 1; l < 4; l++)
+  for (int w = 1; w < 8; w++)
     for (int k = 0; k < K + 2; k++) {
-      const int k2 = std::min(k + (1 << (l - 1)), K + 1);
+      const int k2 = std::min(k + w, K + 1);
       for (int cl = 0; cl < NC; cl++)
-        ptab[l * lv + (size_t)k * NC + cl] = std::max(ptab[(l - 1) * lv + (size_t)k * NC + cl], ptab[(l - 1) * lv + (size_t)k2 * NC + cl]);
+        ptab[w * lv + (size_t)k * NC + cl] = std::max(ptab[(w - 1) * lv + (size_t)k * NC + cl], ptab[(size_t)k2 * NC + cl]);
     }
 }
 

@@ -299,22 +299,20 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       for (int t = t0; t <= t1; t++)
         if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
     // ---- bounded tiles: one warp per tile, lanes over its class runs ----
-    // pmax is a sparse table [level][knot][class]: level l holds the maximum over knots k .. k+2^l-1
+    // pmax = [extra knots 0..7][first knot][class]: maximum over knots k .. k+extra, one load per (run, candidate)
     if (WITHN && W.bmask) {
       const double *__restrict__ pm = P.pmax;
-      const unsigned ncls = (unsigned)P.n_cls, lvl_stride = ((unsigned)P.n_knots + 2u) * ncls;
+      const unsigned ncls = (unsigned)P.n_cls, w_stride = ((unsigned)P.n_knots + 2u) * ncls;
       for (int t = t0 + warp; t <= t1; t += kScanWarps) {
         const int jb = (s_tile[t - t0] >> 20) & 7;
         if (jb == 0) continue;
         const int nr = __ldg(tnrun + t);
         const int *__restrict__ rl = trun + (size_t)t * kTile;
-        unsigned o1[4], o2[4];
+        const double *pj[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          const unsigned kr = W.kr[t - t0][j], ka = kr & 0xFF, ex = kr >> 8;
-          const unsigned lv = 31 - __clz(ex + 1);
-          o1[j] = lv * lvl_stride + ka * ncls;
-          o2[j] = lv * lvl_stride + (ka + ex + 1 - (1u << lv)) * ncls;
+          const unsigned kr = W.kr[t - t0][j];
+          pj[j] = pm + ((size_t)(kr >> 8) * w_stride + (size_t)(kr & 0xFF) * ncls);
         }
         for (int r = lane; r < nr; r += 32) {
           const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
@@ -322,8 +320,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             if (j >= jb) break;
-            // fmax drops a NaN operand: tables with NaN pieces carry +inf here (host), never pruned
-            ub[j] = fma(cntd, fmax(__ldg(pm + o1[j] + cl), __ldg(pm + o2[j] + cl)), ub[j]);
+            ub[j] = fma(cntd, __ldg(pj[j] + cl), ub[j]);
           }
         }
       }
@@ -409,17 +406,15 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         else batch_terms_pipelined<1, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
         if (COUNT) nterms += (unsigned long long)(jfull * kB);
       } else if (jfull > 4) {
+        // near tiles: groups of four candidates, each double-buffered across the records of the batch
 #pragma unroll
-        for (int u = 0; u < kB; u++) {
-#pragma unroll
-          for (int g = 0; g < NA; g += 4) {
-            if (g >= jfull) break;
-            const int gs = jfull - g;
-            if (g + 4 <= NA && gs >= 4) group_terms<4>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
-            else if (g + 3 <= NA && gs == 3) group_terms<3>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
-            else if (g + 2 <= NA && gs == 2) group_terms<2>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
-            else group_terms<1>(acc + g, c_alpha.la[row] + g, x0[u], crow[u], inv_step, offm);
-          }
+        for (int g = 0; g < NA; g += 4) {
+          if (g >= jfull) break;
+          const int gs = jfull - g;
+          if (g + 4 <= NA && gs >= 4) batch_terms_pipelined<4, kB>(acc + g, c_alpha.la[row] + g, x0, crow, inv_step, offm);
+          else if (g + 3 <= NA && gs == 3) batch_terms_pipelined<3, kB>(acc + g, c_alpha.la[row] + g, x0, crow, inv_step, offm);
+          else if (g + 2 <= NA && gs == 2) batch_terms_pipelined<2, kB>(acc + g, c_alpha.la[row] + g, x0, crow, inv_step, offm);
+          else batch_terms_pipelined<1, kB>(acc + g, c_alpha.la[row] + g, x0, crow, inv_step, offm);
         }
         if (COUNT) nterms += (unsigned long long)(jfull * kB);
       }

@@ -51,8 +51,8 @@ struct Params {
   const int *tile_lo, *tile_hi;    // [n_pad / kTile] smallest / largest position inside each tile
   const double *logT;              // [65536]
   const double *null_tab;          // [n_cls]
-  const double *pmax;              // [4][n_knots+2][n_cls] level l: upper bound of (spline piece - null) over the knot
-                                   // intervals k .. k+2^l-1 (sparse table for range maxima, class fastest)
+  const double *pmax;              // [8][n_knots+2][n_cls] entry [w][k][c]: upper bound of (spline piece - null) of class c
+                                   // over the knot intervals k .. k+w (class fastest: the lanes of a warp walk class runs)
 };
 
 // One genome instance (observed, or the permutation slots) as class-bucketed tiles.

@@ -153,21 +153,113 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
 // returning S[j] = (N + sum_j) - N with N the window null sum, which the coarse
 // pass (WITHN) accumulates alongside.
 //
-// Pruning by bounds (use_bound, coarse pass only).  A candidate can only matter if it is the
-// strict maximum (sm-search.c:281), so a candidate whose sum is provably below an exactly
-// evaluated one needs no exact value.  For a tile that lies wholly inside the window, on one side
-// of the sweep and wholly inside the cuts of the first jfull <= 4 candidates, the tile's share of
-// those sums is bounded from above by  sum over class runs  count * max_{knots the tile spans}
-// pmax[class][knot]  (pmax = upper bound of the spline piece minus null over its knot interval,
-// host-built), about 100 run visits instead of 2048 site visits per candidate.  The caller
-// checks  bound + tolerance < best exact candidate  and otherwise repeats the pass exactly.
+// Pruning by bounds (coarse pass only).  A candidate can only matter if it is the strict maximum
+// (sm-search.c:281), so a candidate whose sum is provably below an exactly evaluated one needs no
+// exact value.  For a tile that lies wholly inside the window, on one side of the sweep and wholly
+// inside the cuts of its first jb <= 4 candidates, the tile's share of those sums is bounded from
+// above by  sum over class runs  count * max_{knots the tile spans} (spline piece - null)  (P.pmax,
+// host-built): about 100 run visits instead of 2048 site visits per candidate.  The bounds are
+// taken ONCE PER CELL (dev_cell_bounds) for every sweep position the bisection of the cell can
+// visit, so each grid-eval only adds the stored sums to the exact share of its walked tiles; the
+// caller checks  bound + tolerance < best exact candidate  and otherwise repeats the pass exactly.
 struct PhaseScratch {
   int tile[kMaxTilesC];                 // per-tile classification
   int list[kMaxTilesC];                 // tiles that need a per-site walk, in order
   double tn[kMaxTilesC];                // per-tile null sums (WITHN)
-  unsigned short kr[kMaxTilesC][4];     // bounded tiles: first knot | extra knots << 8 per candidate
+  unsigned short kr[kMaxTilesC + 2][4]; // dev_cell_bounds: first knot | extra knots << 8 per candidate
+  unsigned char jbF[kMaxTilesC + 2];    // cell level: leading candidates of the tile that a bound stands for
+  double ubF[4];                        // cell level: bound sums per candidate over those tiles
+  int t0F, t1F, bmF;                    // tile range of the cell's windows; candidates with a bounded tile
   int n_list, bmask;
 };
+
+// Bounds of the far tiles for all grid-evals of one cell: sweep positions in [A.sweep_pos, B.sweep_pos],
+// windows between A's and B's (nearest site, window ends and the D3 shift are monotone in the position).
+__device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, const int *__restrict__ tnrun,
+                                const PtS &A, const PtS &B, double (*red)[kMaxFine + 1], PhaseScratch &W) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sa = A.sweep_pos, sb = B.sweep_pos;
+  const int ws = max(A.wstart, B.wstart), we = min(A.wend, B.wend);      // sites inside every window of the cell
+  const int t0 = min(A.wstart, B.wstart) / kTile, t1 = min(max(A.wend, B.wend) / kTile, t0 + kMaxTilesC + 1);
+  const double *__restrict__ T = P.logT;
+  const double inv_step = P.inv_step, offm = P.off_magic;
+  const int kclamp = P.n_knots + 1;
+  if (threadIdx.x == 0) { W.t0F = t0; W.t1F = t1; W.bmF = 0; }
+  __syncthreads();
+  for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
+    const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+    const bool ins = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
+    int jb = 0;
+    if (ins && (hi < sa || lo > sb)) {
+      const int dnr = hi < sa ? sa - hi : lo - sb;          // smallest / largest distance over the cell's sweeps
+      const int dfar = hi < sa ? sb - lo : hi - sa;
+      int jf = 0;
+#pragma unroll
+      for (int j = 0; j < kCoarse; j++)
+        if (c_alpha.dmax[kCoarse][j] >= dfar) jf = j + 1;
+      // knots the tile spans per candidate (logt and the knot map are monotone).  The bounded
+      // candidates are a prefix: up to 8 knots wide for a candidate whose cut lies well beyond
+      // the tile (far from competitive), 4 for the last one that still covers the tile.
+      const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
+      bool open = true;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const double la = c_alpha.la[kCoarse][j];
+        const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), kclamp);
+        const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), kclamp);
+        const int ex = max(kb - ka, 0);
+        open = open && j < jf && ex <= (j == jf - 1 ? 3 : 7);
+        if (open) jb = j + 1;
+        W.kr[t - t0][j] = (unsigned short)(ka | (min(ex, 7) << 8));
+      }
+      if (jb) atomicOr(&W.bmF, (1 << jb) - 1);
+    }
+    W.jbF[t - t0] = (unsigned char)jb;
+  }
+  __syncthreads();
+  // one warp per tile, lanes over its class runs; pmax = [extra knots 0..7][first knot][class]
+  double ub[4] = {0.0, 0.0, 0.0, 0.0};
+  if (W.bmF) {
+    const double *__restrict__ pm = P.pmax;
+    const unsigned ncls = (unsigned)P.n_cls, w_stride = ((unsigned)P.n_knots + 2u) * ncls;
+    for (int t = t0 + warp; t <= t1; t += kScanWarps) {
+      const int jb = W.jbF[t - t0];
+      if (jb == 0) continue;
+      const int nr = __ldg(tnrun + t);
+      const int *__restrict__ rl = trun + (size_t)t * kTile;
+      const double *pj[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned kr = W.kr[t - t0][j];
+        pj[j] = pm + ((size_t)(kr >> 8) * w_stride + (size_t)(kr & 0xFF) * ncls);
+      }
+      for (int r = lane; r < nr; r += 32) {
+        const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
+        const double cntd = (double)(e >> 20);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (j >= jb) break;
+          ub[j] = fma(cntd, __ldg(pj[j] + cl), ub[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double v = ub[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
+    W.ubF[threadIdx.x] = v;
+  }
+  __syncthreads();
+}
 
 template <int NA, bool COUNT, bool WITHN>
 __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict__ tkey,
@@ -184,7 +276,6 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (j < na_all && R.dnear <= c_alpha.dmax[row][j]) na = j + 1;
   double acc[NA];
   double accn = 0.0;
-  double ub[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < NA; j++) acc[j] = 0.0;
   if (threadIdx.x == 0) W.bmask = 0;
@@ -211,6 +302,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         if (j < na && c_alpha.dmax[row][j] < g) jd = j;
     }
     const int naw = jd;                 // candidates the tile walk (or a bound) accounts for
+    // the cell-level bounds stand for their candidates' whole share of a tile: usable when none of
+    // those candidates is summed directly (windows of at least a few thousand sites)
+    const bool bounds_on = WITHN && use_bound && W.bmF && jd >= min(na, 4);
+    if (bounds_on && threadIdx.x == 0) W.bmask = W.bmF & ((1 << na) - 1);
     if (jd < na) {
       for (int i = iL + (int)threadIdx.x; i <= iR; i += kScanThreads) {
         const int dd = __ldg(P.pos + i) - sweep, d = dd < 0 ? -dd : dd;
@@ -233,7 +328,6 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     }
     // ---- classify the tiles of the window once per pass, one thread per tile (shared table) ----
     // packed: jany | jfull << 8 | inside << 16 | lut << 17 | needed << 19 | jb << 20  (jb = leading candidates bounded)
-    __syncthreads();                      // W.bmask reset above; the previous pass is done with W
     for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
       const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
       const int dlo = lo > sweep ? lo - sweep : sweep - lo, dhi = hi > sweep ? hi - sweep : sweep - hi;
@@ -255,26 +349,9 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       int jb = 0;
       if (WITHN) {
         if (ins) W.tn[t - t0] = __ldg(tnull + t);
-        if (use_bound && ins && dnr > 0 && jf >= 1) {
-          // knots the tile spans per candidate (logt and the knot map are monotone).  The bounded
-          // candidates are a prefix: up to 8 knots wide for a candidate whose cut lies well beyond
-          // the tile (far from competitive), 4 for the last one that still covers the tile.
-          const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
-          bool open = true;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const double la = c_alpha.la[row][j];
-            const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), (int)kclamp);
-            const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), (int)kclamp);
-            const int ex = max(kb - ka, 0);
-            open = open && j < jf && ex <= (j == jf - 1 ? 3 : 7);
-            if (open) jb = j + 1;
-            W.kr[t - t0][j] = (unsigned short)(ka | (min(ex, 7) << 8));
-          }
-          if (jb) {
-            atomicOr(&W.bmask, (1 << jb) - 1);
-            needed = ja > jb;                 // candidates left for the walk
-          }
+        if (bounds_on && t >= W.t0F && t <= W.t1F) {
+          jb = min((int)W.jbF[t - W.t0F], jf);       // jf >= jbF by construction (the cell bound used the largest distance)
+          if (jb) needed = ja > jb;                   // candidates left for the walk
         }
       }
       s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (jb << 20);
@@ -298,33 +375,6 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (WITHN && threadIdx.x == 0)
       for (int t = t0; t <= t1; t++)
         if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
-    // ---- bounded tiles: one warp per tile, lanes over its class runs ----
-    // pmax = [extra knots 0..7][first knot][class]: maximum over knots k .. k+extra, one load per (run, candidate)
-    if (WITHN && W.bmask) {
-      const double *__restrict__ pm = P.pmax;
-      const unsigned ncls = (unsigned)P.n_cls, w_stride = ((unsigned)P.n_knots + 2u) * ncls;
-      for (int t = t0 + warp; t <= t1; t += kScanWarps) {
-        const int jb = (s_tile[t - t0] >> 20) & 7;
-        if (jb == 0) continue;
-        const int nr = __ldg(tnrun + t);
-        const int *__restrict__ rl = trun + (size_t)t * kTile;
-        const double *pj[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          const unsigned kr = W.kr[t - t0][j];
-          pj[j] = pm + ((size_t)(kr >> 8) * w_stride + (size_t)(kr & 0xFF) * ncls);
-        }
-        for (int r = lane; r < nr; r += 32) {
-          const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
-          const double cntd = (double)(e >> 20);
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            if (j >= jb) break;
-            ub[j] = fma(cntd, __ldg(pj[j] + cl), ub[j]);
-          }
-        }
-      }
-    }
     // A warp owns chunks {warp, warp+8, ...} of every tile and walks them in batches of kB:
     // the kB records of the NEXT batch are fetched while the current one is evaluated,
     // the kB log-distances and the coefficient rows of four alphas are each issued together.
@@ -457,14 +507,6 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) accn += __shfl_xor_sync(0xFFFFFFFFu, accn, o);
     if (lane == 0) red[warp][kMaxFine] = accn;
-    static_assert(NA + 4 <= kMaxFine || !WITHN, "bound sums share the reduction buffer with the candidates");
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      double v = ub[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-      if (lane == 0) red[warp][NA + j] = v;
-    }
   }
   __syncthreads();
   if (threadIdx.x < NA) {
@@ -481,9 +523,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (WITHN && threadIdx.x < 4 && ((W.bmask >> threadIdx.x) & 1)) {
       // bounded candidate: exact share of the walked tiles + bound of the others + tolerance for the
       // rounding of both (the terms are O(1e2), a window has < 2e5 of them)
-      double b = 0.0;
-#pragma unroll
-      for (int w = 0; w < kScanWarps; w++) b += red[w][NA + threadIdx.x];
+      const double b = W.ubF[threadIdx.x];
       s = (v + b) + (1e-4 + 1e-9 * (fabs(v) + fabs(b)));
     }
     S[threadIdx.x] = s;
@@ -519,6 +559,17 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   const bool prune = !(flags & kFlagNoPrune);
   unsigned long long nterms = 0;
 
+  if (threadIdx.x == 0) W.bmF = 0;
+  if (prune) {
+    // bounds of the far tiles, once for every position the search of this cell can visit
+    if (threadIdx.x == 0) {
+      dev_init_point(P, t.chr, t.start_pos, A);
+      dev_init_point(P, t.chr, (flags & kFlagSingle) ? t.start_pos : t.end_pos, B);
+    }
+    __syncthreads();
+    dev_cell_bounds(P, trun, tnrun, A, B, red, W);
+  }
+  __syncthreads();
   int pos = t.start_pos;
   for (int step = 0;; step++) {
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----

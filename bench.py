@@ -229,11 +229,20 @@ def main():
     # ---- e2e: host buffers through the public API, H2D/D2H inside the timed region
     e2e_perms = 128         # permutations per end-to-end step (one H2D of the problem, one forward scan, results to host)
 
+    e2e_phase = {"create_h2d": 0.0, "forward_scan": 0.0, "permuted_scans": 0.0, "close": 0.0}
+
     def e2e_step():
+        ta = time.perf_counter()
         s2 = api.Scanner(flat, device=local)
+        tb = time.perf_counter()
         o = s2.scan_chromosome(G)
+        tc = time.perf_counter()
         p, _, _ = s2.scan_permute(o, e2e_perms - 1, G, rng=api.RNG_PHILOX, seed=2, prune=0)
+        td = time.perf_counter()
         s2.close()
+        te_ = time.perf_counter()
+        for k, v in zip(e2e_phase, (tb - ta, tc - tb, td - tc, te_ - td)):
+            e2e_phase[k] += v
         return p
     # bytes that cross PCIe per step, counted from the buffers the library copies:
     #   in : the problem (sites, classes, spline table, null table), the log table, the cell task list,
@@ -244,6 +253,8 @@ def main():
     d2h = n_cells * 56 + n_cells * 12 + 64
     e2e_step()
     barrier()
+    for k in e2e_phase:
+        e2e_phase[k] = 0.0
     t0 = time.perf_counter()
     n_e2e = 3
     for _ in range(n_e2e):
@@ -295,7 +306,8 @@ def main():
                        "set (R x 1.6 MB classes + 1 MB tables) is L2-resident by design (SURVEY.md 8d)"},
             "grid_evals_per_sec": value * n_cells * 12,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "what": f"Scanner(host arrays) + scan_chromosome + scan_permute({e2e_perms} permutations) + results to host"},
+                    "what": f"Scanner(host arrays) + scan_chromosome + scan_permute({e2e_perms} permutations) + results to host",
+                    "phase_ms_per_step": {k: 1e3 * v / n_e2e for k, v in e2e_phase.items()}},
             "gpu_launches": int(st["kernel_launches"]),
             "clocks": clk,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",

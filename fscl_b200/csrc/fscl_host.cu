@@ -129,6 +129,40 @@ struct PermState {
   int n_active = 0, cur = 0;           // d_active[cur] holds the active list
 };
 
+// Device memory comes from the stream-ordered pool of the device with an unlimited release
+// threshold: creating and destroying a context (one per end-to-end call of the Python layer)
+// reuses cached blocks instead of paying cudaMalloc / cudaFree (device-wide synchronisation, tens
+// of ms each once other libraries hold mappings).  Callers free only memory no stream still uses.
+cudaStream_t g_alloc_stream[64] = {};
+
+cudaStream_t alloc_stream() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (!g_alloc_stream[dev]) {
+    cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
+  return g_alloc_stream[dev];
+}
+
+template <class T>
+cudaError_t dev_malloc(T **p, size_t bytes) {
+  cudaStream_t s = alloc_stream();
+  cudaError_t e = cudaMallocAsync((void **)p, bytes ? bytes : 1, s);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(s);
+}
+
+// freed in the order of the stream that used the memory last
+void dev_free(void *p, cudaStream_t s) {
+  if (p) cudaFreeAsync(p, s);
+}
+
 struct Ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -170,11 +204,11 @@ struct Ctx {
 int ensure_tasks(Ctx *c, size_t n) {
   if (n <= c->tasks_cap) return FSCL_OK;
   size_t cap = std::max<size_t>(n, c->tasks_cap * 2);
-  if (c->d_tasks) cudaFree(c->d_tasks);
-  if (c->d_out) cudaFree(c->d_out);
+  if (c->d_tasks) dev_free(c->d_tasks, c->stream);
+  if (c->d_out) dev_free(c->d_out, c->stream);
   c->d_tasks = nullptr; c->d_out = nullptr; c->tasks_cap = 0;
-  CK(cudaMalloc(&c->d_tasks, cap * sizeof(Task)));
-  CK(cudaMalloc(&c->d_out, cap * sizeof(OutPt)));
+  CK(dev_malloc(&c->d_tasks, cap * sizeof(Task)));
+  CK(dev_malloc(&c->d_out, cap * sizeof(OutPt)));
   c->tasks_cap = cap;
   return FSCL_OK;
 }
@@ -217,48 +251,51 @@ void build_piece_maxima(const double *coefC, int NC, int K, double step, std::ve
       const double mag = std::fabs(c3) + xm * (std::fabs(c2) + xm * (std::fabs(c1) + xm * std::fabs(c0)));
       out = m + 1e-11 * mag + 1e-300;
     }
-  // range maxima over knots k .. k+w for w = 0..7, [w][knot][class]; windows are clipped at the last row
+  // sparse table for range maxima over knots, [level][knot][class], level l = knots k .. k+2^l-1
+  // (clipped at the last row); floor(log2(K+2))+1 levels cover every range of the K+2 rows
   const size_t lv = (size_t)(K + 2) * NC;
-  ptab.assign(8 * lv, 0.0);
+  int n_lv = 1;
+  while ((2 << (n_lv - 1)) <= K + 2) n_lv++;
+  ptab.assign((size_t)n_lv * lv, 0.0);
   for (int k = 0; k < K + 2; k++)
     for (int cl = 0; cl < NC; cl++) ptab[(size_t)k * NC + cl] = pmax[(size_t)cl * (K + 2) + k];
-  for (int w = 1; w < 8; w++)
+  for (int l = 1; l < n_lv; l++)
     for (int k = 0; k < K + 2; k++) {
-      const int k2 = std::min(k + w, K + 1);
+      const int k2 = std::min(k + (1 << (l - 1)), K + 1);
       for (int cl = 0; cl < NC; cl++)
-        ptab[w * lv + (size_t)k * NC + cl] = std::max(ptab[(w - 1) * lv + (size_t)k * NC + cl], ptab[(size_t)k2 * NC + cl]);
+        ptab[l * lv + (size_t)k * NC + cl] = std::max(ptab[(l - 1) * lv + (size_t)k * NC + cl], ptab[(l - 1) * lv + (size_t)k2 * NC + cl]);
     }
 }
 
-void free_tiles(TileSet &t) {
-  cudaFree(t.key); cudaFree(t.pos); cudaFree(t.tnull); cudaFree(t.run); cudaFree(t.nrun);
+void free_tiles(TileSet &t, cudaStream_t s) {
+  dev_free(t.key, s); dev_free(t.pos, s); dev_free(t.tnull, s); dev_free(t.run, s); dev_free(t.nrun, s);
   t = TileSet{};
 }
 
 int alloc_tiles(TileSet &t, int slots, int n_pad) {
-  CK(cudaMalloc(&t.tnull, (size_t)slots * (n_pad / kTile) * sizeof(double)));
-  CK(cudaMalloc(&t.nrun, (size_t)slots * (n_pad / kTile) * sizeof(int)));
-  CK(cudaMalloc(&t.key, (size_t)slots * n_pad * sizeof(int)));
-  CK(cudaMalloc(&t.pos, (size_t)slots * n_pad * sizeof(int)));
-  CK(cudaMalloc(&t.run, (size_t)slots * n_pad * sizeof(int)));
+  CK(dev_malloc(&t.tnull, (size_t)slots * (n_pad / kTile) * sizeof(double)));
+  CK(dev_malloc(&t.nrun, (size_t)slots * (n_pad / kTile) * sizeof(int)));
+  CK(dev_malloc(&t.key, (size_t)slots * n_pad * sizeof(int)));
+  CK(dev_malloc(&t.pos, (size_t)slots * n_pad * sizeof(int)));
+  CK(dev_malloc(&t.run, (size_t)slots * n_pad * sizeof(int)));
   return FSCL_OK;
 }
 
 int ensure_slots(Ctx *c, int slots) {
   if (slots <= c->max_slots) return FSCL_OK;
-  if (c->d_pcls) cudaFree(c->d_pcls);
-  if (c->d_scratch) cudaFree(c->d_scratch);
-  if (c->d_blkoff) cudaFree(c->d_blkoff);
-  if (c->d_blkcnt) cudaFree(c->d_blkcnt);
+  if (c->d_pcls) dev_free(c->d_pcls, c->stream);
+  if (c->d_scratch) dev_free(c->d_scratch, c->stream);
+  if (c->d_blkoff) dev_free(c->d_blkoff, c->stream);
+  if (c->d_blkcnt) dev_free(c->d_blkcnt, c->stream);
   c->d_blkcnt = nullptr;
-  free_tiles(c->ts);
+  free_tiles(c->ts, c->stream);
   c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
   { int rc = alloc_tiles(c->ts, slots, c->n_pad); if (rc) return rc; }
-  CK(cudaMalloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
+  CK(dev_malloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
   c->ts.cls = c->d_pcls; c->ts.cls_stride = (size_t)c->n;
-  CK(cudaMalloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
-  CK(cudaMalloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
-  CK(cudaMalloc(&c->d_blkcnt, (size_t)(slots + 1) * sizeof(int)));
+  CK(dev_malloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
+  CK(dev_malloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
+  CK(dev_malloc(&c->d_blkcnt, (size_t)(slots + 1) * sizeof(int)));
   c->max_slots = slots;
   return FSCL_OK;
 }
@@ -490,23 +527,23 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaEventCreate(&c->ev1));
   CK(cudaEventCreate(&c->ev2));
   CK(cudaEventCreate(&c->ev3));
-  CK(cudaMalloc(&c->d_pos, sizeof(int) * c->n));
-  CK(cudaMalloc(&c->d_cls0, sizeof(int) * c->n));
-  CK(cudaMalloc(&c->d_chr_start, sizeof(int) * c->n_chr));
-  CK(cudaMalloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
-  CK(cudaMalloc(&c->d_coefC, sizeof(double) * coefC.size()));
+  CK(dev_malloc(&c->d_pos, sizeof(int) * c->n));
+  CK(dev_malloc(&c->d_cls0, sizeof(int) * c->n));
+  CK(dev_malloc(&c->d_chr_start, sizeof(int) * c->n_chr));
+  CK(dev_malloc(&c->d_chr_nsnps, sizeof(int) * c->n_chr));
+  CK(dev_malloc(&c->d_coefC, sizeof(double) * coefC.size()));
   { int rc = alloc_tiles(c->ts0, 1, c->n_pad); if (rc) return rc; }
   c->ts0.cls = c->d_cls0; c->ts0.cls_stride = 0;
-  CK(cudaMalloc(&c->d_pmax, sizeof(double) * pmax.size()));
+  CK(dev_malloc(&c->d_pmax, sizeof(double) * pmax.size()));
   CK(cudaMemcpy(c->d_pmax, pmax.data(), sizeof(double) * pmax.size(), cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_tile_lo, sizeof(int) * n_tiles));
-  CK(cudaMalloc(&c->d_tile_hi, sizeof(int) * n_tiles));
+  CK(dev_malloc(&c->d_tile_lo, sizeof(int) * n_tiles));
+  CK(dev_malloc(&c->d_tile_hi, sizeof(int) * n_tiles));
   CK(cudaMemcpy(c->d_tile_lo, tlo.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_tile_hi, thi.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
-  CK(cudaMalloc(&c->d_logT, sizeof(double) * 65536));
-  CK(cudaMalloc(&c->d_null, sizeof(double) * NC));
-  CK(cudaMalloc(&c->d_terms, 2 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
-  CK(cudaMalloc(&c->d_chr_end, sizeof(int) * c->n));
+  CK(dev_malloc(&c->d_logT, sizeof(double) * 65536));
+  CK(dev_malloc(&c->d_null, sizeof(double) * NC));
+  CK(dev_malloc(&c->d_terms, 2 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
+  CK(dev_malloc(&c->d_chr_end, sizeof(int) * c->n));
   CK(cudaMemcpy(c->d_chr_end, c->chr_end_index.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemset(c->d_terms, 0, 2 * sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
@@ -537,14 +574,15 @@ extern "C" void fscl_destroy(void *ctx) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_pos); cudaFree(c->d_cls0); cudaFree(c->d_chr_start); cudaFree(c->d_chr_nsnps);
-  cudaFree(c->d_coefC); free_tiles(c->ts0); free_tiles(c->ts); cudaFree(c->d_pmax);
-  cudaFree(c->d_tile_lo); cudaFree(c->d_tile_hi); cudaFree(c->d_logT); cudaFree(c->d_null); cudaFree(c->d_terms);
-  cudaFree(c->d_pcls); cudaFree(c->d_scratch); cudaFree(c->d_blocks); cudaFree(c->d_blkoff);
-  cudaFree(c->d_tasks); cudaFree(c->d_out); cudaFree(c->d_matrix);
-  cudaFree(c->d_blkcnt); cudaFree(c->d_chr_end); cudaFree(c->d_active[0]); cudaFree(c->d_active[1]);
-  cudaFree(c->d_pt_chr); cudaFree(c->d_pt_sweep); cudaFree(c->d_pp); cudaFree(c->d_pn); cudaFree(c->d_pf);
-  cudaFree(c->d_pt_clr); cudaFree(c->d_pclr); cudaFree(c->d_small);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  dev_free(c->d_pos, c->stream); dev_free(c->d_cls0, c->stream); dev_free(c->d_chr_start, c->stream); dev_free(c->d_chr_nsnps, c->stream);
+  dev_free(c->d_coefC, c->stream); free_tiles(c->ts0, c->stream); free_tiles(c->ts, c->stream); dev_free(c->d_pmax, c->stream);
+  dev_free(c->d_tile_lo, c->stream); dev_free(c->d_tile_hi, c->stream); dev_free(c->d_logT, c->stream); dev_free(c->d_null, c->stream); dev_free(c->d_terms, c->stream);
+  dev_free(c->d_pcls, c->stream); dev_free(c->d_scratch, c->stream); dev_free(c->d_blocks, c->stream); dev_free(c->d_blkoff, c->stream);
+  dev_free(c->d_tasks, c->stream); dev_free(c->d_out, c->stream); dev_free(c->d_matrix, c->stream);
+  dev_free(c->d_blkcnt, c->stream); dev_free(c->d_chr_end, c->stream); dev_free(c->d_active[0], c->stream); dev_free(c->d_active[1], c->stream);
+  dev_free(c->d_pt_chr, c->stream); dev_free(c->d_pt_sweep, c->stream); dev_free(c->d_pp, c->stream); dev_free(c->d_pn, c->stream); dev_free(c->d_pf, c->stream);
+  dev_free(c->d_pt_clr, c->stream); dev_free(c->d_pclr, c->stream); dev_free(c->d_small, c->stream);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -617,10 +655,10 @@ extern "C" int fscl_scan_chromosome(void *ctx, int G, fscl_pt_t *out, int cap, i
 // --------------------------------------------------------------------------- permutations
 static int upload_blocks(Ctx *c, const std::vector<int4> &blocks, const std::vector<int> &off) {
   if (blocks.size() > c->blocks_cap) {
-    if (c->d_blocks) cudaFree(c->d_blocks);
+    if (c->d_blocks) dev_free(c->d_blocks, c->stream);
     c->d_blocks = nullptr; c->blocks_cap = 0;
     size_t cap = blocks.size() * 2 + 1024;
-    CK(cudaMalloc(&c->d_blocks, cap * sizeof(int4)));
+    CK(dev_malloc(&c->d_blocks, cap * sizeof(int4)));
     c->blocks_cap = cap;
   }
   if (!blocks.empty())
@@ -685,19 +723,19 @@ extern "C" int fscl_block_permute(void *ctx, const fscl_permute_opts_t *o, int t
 static int ensure_pts(Ctx *c, int n_pts, bool want_clr) {
   if (n_pts > c->pts_cap) {
     for (int *&p : {std::ref(c->d_active[0]), std::ref(c->d_active[1]), std::ref(c->d_pt_chr), std::ref(c->d_pt_sweep),
-                    std::ref(c->d_pp), std::ref(c->d_pn), std::ref(c->d_pf)}) { if (p) cudaFree(p); p = nullptr; }
-    if (c->d_pt_clr) cudaFree(c->d_pt_clr);
-    if (c->d_pclr) cudaFree(c->d_pclr);
+                    std::ref(c->d_pp), std::ref(c->d_pn), std::ref(c->d_pf)}) { if (p) dev_free(p, c->stream); p = nullptr; }
+    if (c->d_pt_clr) dev_free(c->d_pt_clr, c->stream);
+    if (c->d_pclr) dev_free(c->d_pclr, c->stream);
     c->d_pt_clr = nullptr; c->d_pclr = nullptr; c->pclr_alloc = false; c->pts_cap = 0;
     const size_t b = sizeof(int) * (size_t)n_pts;
-    CK(cudaMalloc(&c->d_active[0], b)); CK(cudaMalloc(&c->d_active[1], b));
-    CK(cudaMalloc(&c->d_pt_chr, b)); CK(cudaMalloc(&c->d_pt_sweep, b));
-    CK(cudaMalloc(&c->d_pp, b)); CK(cudaMalloc(&c->d_pn, b)); CK(cudaMalloc(&c->d_pf, b));
-    CK(cudaMalloc(&c->d_pt_clr, sizeof(double) * (size_t)n_pts));
+    CK(dev_malloc(&c->d_active[0], b)); CK(dev_malloc(&c->d_active[1], b));
+    CK(dev_malloc(&c->d_pt_chr, b)); CK(dev_malloc(&c->d_pt_sweep, b));
+    CK(dev_malloc(&c->d_pp, b)); CK(dev_malloc(&c->d_pn, b)); CK(dev_malloc(&c->d_pf, b));
+    CK(dev_malloc(&c->d_pt_clr, sizeof(double) * (size_t)n_pts));
     c->pts_cap = n_pts;
   }
   if (want_clr && !c->pclr_alloc) {
-    CK(cudaMalloc(&c->d_pclr, sizeof(float) * FSCL_NULL_SAVE * (size_t)c->pts_cap));
+    CK(dev_malloc(&c->d_pclr, sizeof(float) * FSCL_NULL_SAVE * (size_t)c->pts_cap));
     c->pclr_alloc = true;
   }
   return FSCL_OK;
@@ -705,9 +743,9 @@ static int ensure_pts(Ctx *c, int n_pts, bool want_clr) {
 
 static int ensure_small(Ctx *c, int n) {
   if (n <= c->small_cap) return FSCL_OK;
-  if (c->d_small) cudaFree(c->d_small);
+  if (c->d_small) dev_free(c->d_small, c->stream);
   c->d_small = nullptr; c->small_cap = 0;
-  CK(cudaMalloc(&c->d_small, sizeof(int) * (5 * (size_t)n + 8)));
+  CK(dev_malloc(&c->d_small, sizeof(int) * (5 * (size_t)n + 8)));
   c->small_cap = n;
   return FSCL_OK;
 }
@@ -770,9 +808,9 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
   if (!dm) {
     const size_t need = (size_t)R * na;
     if (need > c->matrix_cap) {
-      if (c->d_matrix) cudaFree(c->d_matrix);
+      if (c->d_matrix) dev_free(c->d_matrix, c->stream);
       c->d_matrix = nullptr; c->matrix_cap = 0;
-      CK(cudaMalloc(&c->d_matrix, need * sizeof(double)));
+      CK(dev_malloc(&c->d_matrix, need * sizeof(double)));
       c->matrix_cap = need;
     }
     dm = c->d_matrix;
@@ -786,9 +824,9 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
     rc = ensure_slots(c, ns); if (rc) return rc;
     const int stride = c->n / 4 + 1024;                       // block-list capacity per permutation
     if ((size_t)ns * stride > c->blocks_cap) {
-      if (c->d_blocks) cudaFree(c->d_blocks);
+      if (c->d_blocks) dev_free(c->d_blocks, c->stream);
       c->d_blocks = nullptr; c->blocks_cap = 0;
-      CK(cudaMalloc(&c->d_blocks, (size_t)ns * stride * sizeof(int4)));
+      CK(dev_malloc(&c->d_blocks, (size_t)ns * stride * sizeof(int4)));
       c->blocks_cap = (size_t)ns * stride;
     }
     CK(cudaMemcpyAsync(d_tl, tl.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
@@ -994,9 +1032,9 @@ static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, i
   if (!dm) {
     size_t need = (size_t)R * na;
     if (need > c->matrix_cap) {
-      if (c->d_matrix) cudaFree(c->d_matrix);
+      if (c->d_matrix) dev_free(c->d_matrix, c->stream);
       c->d_matrix = nullptr; c->matrix_cap = 0;
-      CK(cudaMalloc(&c->d_matrix, need * sizeof(double)));
+      CK(dev_malloc(&c->d_matrix, need * sizeof(double)));
       c->matrix_cap = need;
     }
     dm = c->d_matrix;
@@ -1097,9 +1135,9 @@ extern "C" int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *o, i
   if (ensure_slots(c, 1) || ensure_small(c, 1)) return -1;
   const int stride = c->n / 4 + 1024;
   if ((size_t)stride > c->blocks_cap) {
-    if (c->d_blocks) cudaFree(c->d_blocks);
+    if (c->d_blocks) dev_free(c->d_blocks, c->stream);
     c->d_blocks = nullptr; c->blocks_cap = 0;
-    if (cudaMalloc(&c->d_blocks, (size_t)stride * sizeof(int4)) != cudaSuccess) { fail(FSCL_ERR_CUDA, "cudaMalloc"); return -1; }
+    if (dev_malloc(&c->d_blocks, (size_t)stride * sizeof(int4)) != cudaSuccess) { fail(FSCL_ERR_CUDA, "cudaMalloc"); return -1; }
     c->blocks_cap = stride;
   }
   const int sc = c->small_cap;
@@ -1362,7 +1400,7 @@ extern "C" int fscl_fp64_peak(int device, double *tflops) {
   CK(cudaGetDeviceProperties(&prop, device));
   int grid = prop.multiProcessorCount * 8, iters = 1 << 16;
   double *d = nullptr;
-  CK(cudaMalloc(&d, sizeof(double) * grid * 256));
+  CK(dev_malloc(&d, sizeof(double) * grid * 256));
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
   double best = 0;
@@ -1376,7 +1414,7 @@ extern "C" int fscl_fp64_peak(int device, double *tflops) {
     double tf = 2.0 * 8.0 * iters * (double)grid * 256.0 / (ms * 1e-3) / 1e12;
     if (rep > 0) best = std::max(best, tf);
   }
-  cudaFree(d); cudaEventDestroy(e0); cudaEventDestroy(e1);
+  dev_free(d, 0); cudaEventDestroy(e0); cudaEventDestroy(e1);
   *tflops = best;
   return FSCL_OK;
 }

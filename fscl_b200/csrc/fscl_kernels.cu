@@ -166,7 +166,7 @@ struct PhaseScratch {
   int tile[kMaxTilesC];                 // per-tile classification
   int list[kMaxTilesC];                 // tiles that need a per-site walk, in order
   double tn[kMaxTilesC];                // per-tile null sums (WITHN)
-  unsigned short kr[kMaxTilesC + 2][4]; // dev_cell_bounds: first knot | extra knots << 8 per candidate
+  unsigned kr[kMaxTilesC + 2][4];       // dev_cell_bounds: first knot | extra knots << 16 per candidate
   unsigned char jbF[kMaxTilesC + 2];    // cell level: leading candidates of the tile that a bound stands for
   double ubF[4];                        // cell level: bound sums per candidate over those tiles
   int t0F, t1F, bmF;                    // tile range of the cell's windows; candidates with a bounded tile
@@ -190,16 +190,20 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
     const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
     const bool ins = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
     int jb = 0;
-    if (ins && (hi < sa || lo > sb)) {
-      const int dnr = hi < sa ? sa - hi : lo - sb;          // smallest / largest distance over the cell's sweeps
-      const int dfar = hi < sa ? sb - lo : hi - sa;
+    if (ins) {
+      // smallest / largest distance of a tile site over the cell's sweep positions (0 when a sweep
+      // can fall inside the tile: logt(0) = T[0], the lowest knot the candidate can reach)
+      const int dnr = hi < sa ? sa - hi : (lo > sb ? lo - sb : 0);
+      const int dfar = max(sb - lo, hi - sa);
       int jf = 0;
 #pragma unroll
       for (int j = 0; j < kCoarse; j++)
         if (c_alpha.dmax[kCoarse][j] >= dfar) jf = j + 1;
       // knots the tile spans per candidate (logt and the knot map are monotone).  The bounded
-      // candidates are a prefix: up to 8 knots wide for a candidate whose cut lies well beyond
-      // the tile (far from competitive), 4 for the last one that still covers the tile.
+      // candidates are a prefix.  How wide a knot range a bound may span depends on how far beyond
+      // the tile the candidate's cut lies (the further, the deeper in the saturated part of the
+      // sweep model and the further from competitive): kLimLast+1 knots for the last candidate that
+      // still covers the tile, kLimMid+1 for the two before it, any width for the rest.
       const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
       bool open = true;
 #pragma unroll
@@ -208,30 +212,34 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
         const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), kclamp);
         const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), kclamp);
         const int ex = max(kb - ka, 0);
-        open = open && j < jf && ex <= (j == jf - 1 ? 3 : 7);
+        const int lim = j == jf - 1 ? kLimLast : (j >= jf - 3 ? kLimMid : 0x7FFF);
+        open = open && j < jf && ex <= lim;
         if (open) jb = j + 1;
-        W.kr[t - t0][j] = (unsigned short)(ka | (min(ex, 7) << 8));
+        W.kr[t - t0][j] = (unsigned)ka | ((unsigned)ex << 16);
       }
       if (jb) atomicOr(&W.bmF, (1 << jb) - 1);
     }
     W.jbF[t - t0] = (unsigned char)jb;
   }
   __syncthreads();
-  // one warp per tile, lanes over its class runs; pmax = [extra knots 0..7][first knot][class]
+  // one warp per tile, lanes over its class runs; pmax = sparse table [level][first knot][class],
+  // level l = maximum over knots k .. k+2^l-1: a range maximum is the larger of two entries
   double ub[4] = {0.0, 0.0, 0.0, 0.0};
   if (W.bmF) {
     const double *__restrict__ pm = P.pmax;
-    const unsigned ncls = (unsigned)P.n_cls, w_stride = ((unsigned)P.n_knots + 2u) * ncls;
+    const unsigned ncls = (unsigned)P.n_cls, l_stride = ((unsigned)P.n_knots + 2u) * ncls;
     for (int t = t0 + warp; t <= t1; t += kScanWarps) {
       const int jb = W.jbF[t - t0];
       if (jb == 0) continue;
       const int nr = __ldg(tnrun + t);
       const int *__restrict__ rl = trun + (size_t)t * kTile;
-      const double *pj[4];
+      const double *p1[4], *p2[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const unsigned kr = W.kr[t - t0][j];
-        pj[j] = pm + ((size_t)(kr >> 8) * w_stride + (size_t)(kr & 0xFF) * ncls);
+        const unsigned kr = W.kr[t - t0][j], ka = kr & 0xFFFF, ex = kr >> 16;
+        const unsigned lv = 31 - __clz(ex + 1);
+        p1[j] = pm + ((size_t)lv * l_stride + (size_t)ka * ncls);
+        p2[j] = pm + ((size_t)lv * l_stride + (size_t)(ka + ex + 1 - (1u << lv)) * ncls);
       }
       for (int r = lane; r < nr; r += 32) {
         const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
@@ -239,7 +247,8 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           if (j >= jb) break;
-          ub[j] = fma(cntd, __ldg(pj[j] + cl), ub[j]);
+          // fmax drops a NaN operand: tables with NaN pieces carry +inf here (host), never pruned
+          ub[j] = fma(cntd, fmax(__ldg(p1[j] + cl), __ldg(p2[j] + cl)), ub[j]);
         }
       }
     }

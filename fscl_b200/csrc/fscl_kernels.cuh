@@ -28,7 +28,7 @@ constexpr int kRows = kCoarse + 1;  // fine lists for each coarse argmax + the c
 #define FSCL_MINBLK 2
 #endif
 #ifndef FSCL_TILE
-#define FSCL_TILE 2048
+#define FSCL_TILE 1024
 #endif
 #ifndef FSCL_KB
 #define FSCL_KB 4
@@ -38,7 +38,17 @@ constexpr int kScanMinBlocks = FSCL_MINBLK;   // up to 128 registers: batch stat
 constexpr int kTile = FSCL_TILE;         // sites per class-bucketed tile (<= 4096: 12-bit index in the key)
 constexpr int kScanWarps = kScanThreads / 32;
 constexpr int kPermThreads = 1024;
-constexpr int kDirect = 512;     // sites either side of the nearest one that narrow-cut candidates are summed from directly
+#ifndef FSCL_LIM_LAST
+#define FSCL_LIM_LAST 5
+#endif
+#ifndef FSCL_LIM_MID
+#define FSCL_LIM_MID 7
+#endif
+constexpr int kLimLast = FSCL_LIM_LAST, kLimMid = FSCL_LIM_MID;   // extra knots a bound may span (dev_cell_bounds)
+#ifndef FSCL_DIRECT
+#define FSCL_DIRECT 128
+#endif
+constexpr int kDirect = FSCL_DIRECT;     // sites either side of the nearest one that narrow-cut candidates are summed from directly
 
 struct Params {
   int n_snps, n_pad, n_chr, n_cls, n_knots, eval_range, bp_resl;
@@ -51,8 +61,9 @@ struct Params {
   const int *tile_lo, *tile_hi;    // [n_pad / kTile] smallest / largest position inside each tile
   const double *logT;              // [65536]
   const double *null_tab;          // [n_cls]
-  const double *pmax;              // [8][n_knots+2][n_cls] entry [w][k][c]: upper bound of (spline piece - null) of class c
-                                   // over the knot intervals k .. k+w (class fastest: the lanes of a warp walk class runs)
+  const double *pmax;              // [levels][n_knots+2][n_cls] entry [l][k][c]: upper bound of (spline piece - null) of class c
+                                   // over the knot intervals k .. k+2^l-1 (sparse table for range maxima; class fastest:
+                                   // the lanes of a warp walk class runs)
 };
 
 // One genome instance (observed, or the permutation slots) as class-bucketed tiles.

@@ -1,0 +1,8 @@
+# quick parity subset + bench of the main library and every build/var/lib_*.so (each variant also runs the parity subset)
+run() { python bench.py --steps 3 --warmup 3 --no-pruned-run --no-cpu-baseline 2>gpurun_out/bench_quick.err | tail -1 > gpurun_out/bench_$1.json; python -c "
+import json,sys; d=json.load(open('gpurun_out/bench_$1.json')); print('$1', 'value %.1f' % d['value'],'e2e %.1f' % d['e2e']['value'], d['e2e'].get('phase_ms_per_step'), 'frac %.3f' % d['roofline']['frac'], 'kernel_ms %.1f' % d['roofline']['kernel_ms'], 'terms %.3g' % d['roofline']['snp_terms_per_launch'], 'redo', d['roofline'].get('coarse_passes_repeated_exactly'))"; }
+run main
+for v in build/var/lib_*.so; do
+  FSCL_B200_LIB=$PWD/$v timeout 600 python -m pytest tests/test_gpu_scale.py -m gpu -x -q -k "pruning or spot" 2>&1 | tail -1
+  FSCL_B200_LIB=$PWD/$v run $(basename $v .so)
+done

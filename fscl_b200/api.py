@@ -69,7 +69,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
-           "fscl_set_exact_candidates"]
+           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek"]
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load_library(path=LIB_PATH):
     L.fscl_perm_round_score.argtypes = [vp, vp, C.c_int64, vp, vp]
     L.fscl_perm_round_commit.argtypes = [vp, vp]
     L.fscl_perm_end.argtypes = [vp, vp]
+    L.fscl_perm_snapshot.argtypes = [vp, vp]
+    L.fscl_perm_seek.argtypes = [vp, ci]
     L.fscl_bench_scan.argtypes = [vp, ci, ci, ci, vp, vp]
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_set_exact_candidates.argtypes = [vp, ci]
@@ -328,6 +330,36 @@ class Scanner:
         _check(self.L.fscl_scan_permute(self._ctx, pts.ctypes.data, len(pts), C.byref(o),
                                         clr.ctypes.data if save_clr else None, C.byref(st)))
         return pts, st.asdict(), clr
+
+    def scan_permute_rounds(self, pts, n_permute, G, save_clr=False, start_t=0, clr=None, max_rounds=None, **kw):
+        """The permutation test round by round, interruptible and resumable (counter-based stream).
+
+        Starts at permutation ``start_t`` with the counters found in ``pts`` (and the stored CLRs in
+        ``clr``), runs at most ``max_rounds`` rounds and returns ``(pts, stats, clr, t_next)``:
+        feeding these back as ``pts, clr, start_t=t_next`` continues the test, and the final result
+        equals an uninterrupted ``scan_permute`` bit for bit.  ``t_next > n_permute`` means finished."""
+        pts = np.ascontiguousarray(pts.copy())
+        o = self.permute_opts(n_permute, G, **kw)
+        if save_clr and clr is None:
+            clr = np.zeros((len(pts), NULL_SAVE), dtype=np.float32)
+        elif clr is not None:
+            clr = np.ascontiguousarray(clr.copy())
+        _check(self.L.fscl_perm_begin(self._ctx, pts.ctypes.data, len(pts), C.byref(o),
+                                      clr.ctypes.data if clr is not None else None))
+        if start_t:
+            _check(self.L.fscl_perm_seek(self._ctx, int(start_t)))
+        R, na, rounds = C.c_int(0), C.c_int(0), 0
+        while max_rounds is None or rounds < max_rounds:
+            _check(self.L.fscl_perm_round_score(self._ctx, None, 0, C.byref(R), C.byref(na)))
+            if R.value == 0:
+                break
+            _check(self.L.fscl_perm_round_commit(self._ctx, None))
+            rounds += 1
+        t_next = C.c_int32(0)
+        _check(self.L.fscl_perm_snapshot(self._ctx, C.byref(t_next)))
+        st = fscl_stats_t()
+        _check(self.L.fscl_perm_end(self._ctx, C.byref(st)))
+        return pts, st.asdict(), clr, t_next.value
 
     def scan_permute_sharded(self, pts, n_permute, G, rank, world, allreduce, matrix, matrix_ptr, save_clr=False,
                              **kw):

@@ -1107,6 +1107,42 @@ extern "C" int fscl_perm_end(void *ctx, fscl_stats_t *stats_out) {
   return FSCL_OK;
 }
 
+// Bring the caller's pts / permute_clr up to date between rounds without ending the test
+// (what the reference's SIGINT handler reads, scan-chromosome.c:557-569; also the checkpoint).
+extern "C" int fscl_perm_snapshot(void *ctx, int32_t *t_next_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !c->perm.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
+  if (c->perm.on_device) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int rc = device_end(c);
+    if (rc) return rc;
+  }
+  if (t_next_out) *t_next_out = c->perm.t_next;
+  return FSCL_OK;
+}
+
+// Continue a test at permutation t_next (right after fscl_perm_begin): the counters and finished
+// flags were taken from pts by fscl_perm_begin; the stored permuted CLRs are re-loaded here.
+// Counter-based stream only -- a sequential rand() stream cannot be re-entered in the middle.
+extern "C" int fscl_perm_seek(void *ctx, int32_t t_next) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !c->perm.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
+  PermState &S = c->perm;
+  if (S.src.sequential()) return fail(FSCL_ERR_ARG, "only the counter-based stream can resume");
+  if (t_next < 0 || S.t_next != 0) return fail(FSCL_ERR_ARG, "seek is only valid right after fscl_perm_begin");
+  S.t_next = t_next;
+  if (S.on_device && S.permute_clr) {
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < S.n_pts; i++) {
+      const int m = std::min(S.pts[i].permute_n, FSCL_NULL_SAVE);
+      if (m > 0) CK(cudaMemcpy(c->d_pclr + (size_t)i * FSCL_NULL_SAVE, S.permute_clr + (size_t)i * FSCL_NULL_SAVE,
+                               sizeof(float) * m, cudaMemcpyHostToDevice));
+    }
+  }
+  return FSCL_OK;
+}
+
 extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *o,
                                  float *permute_clr, fscl_stats_t *stats_out) {
   Ctx *c = (Ctx *)ctx;

@@ -486,6 +486,11 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           if (j >= jany) break;
           const double la = c_alpha.la[row][j];
           const int dm = c_alpha.dmax[row][j];
+          // the cuts shrink with j: once no site of the batch is inside one, none is inside the next
+          bool any = false;
+#pragma unroll
+          for (int u = 0; u < kB; u++) any = any || dq[u] <= dm;
+          if (!__any_sync(0xFFFFFFFFu, any)) break;
           double x[kB], c0[kB], c1[kB], c2[kB], c3[kB];
 #pragma unroll
           for (int u = 0; u < kB; u++) {

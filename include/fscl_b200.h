@@ -138,6 +138,14 @@ int fscl_perm_begin(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opt
 int fscl_perm_round_score(void *ctx, double *d_matrix, int64_t cap, int *R_out, int *n_active_out);
 int fscl_perm_round_commit(void *ctx, const double *d_matrix);
 int fscl_perm_end(void *ctx, fscl_stats_t *stats);
+/* Between rounds: bring pts / permute_clr up to date without ending the test (what the reference's
+ * SIGINT handler dumps, scan-chromosome.c:557-569; also the content of a checkpoint).
+ * *t_next_out = index of the next permutation to be scored. */
+int fscl_perm_snapshot(void *ctx, int32_t *t_next_out);
+/* Right after fscl_perm_begin: continue at permutation t_next with the counters, finished flags
+ * and stored CLRs found in pts / permute_clr (a checkpoint).  Counter-based stream only: the
+ * result equals an uninterrupted run bit for bit. */
+int fscl_perm_seek(void *ctx, int32_t t_next);
 /* Host-side pieces of the path, callable without a device (same code the GPU
  * path runs on the host): alpha candidate tables [12][15] (row 11 = coarse list,
  * sm-search.c:276-296, with the per-alpha distance cut), cell enumeration, the

@@ -149,3 +149,22 @@ def test_device_rounds_equal_host_rounds(api, monkeypatch):
         assert np.array_equal(a[k], b[k])
     assert np.array_equal(ca, cb)
     assert sta["n_scored"] == stb["n_scored"] and a["permute_finished"].sum() > 0
+
+
+def test_permutation_test_resumes_bit_exactly(api):
+    """Checkpoint / resume: stopping after a few rounds and continuing from the
+    snapshot gives the counts, flags and stored CLRs of an uninterrupted run."""
+    tab, flat, G = problem("small50")
+    sc = api.Scanner(flat)
+    obs = sc.scan_chromosome(G)
+    full, _, clr_full = sc.scan_permute(obs, 60, G, save_clr=True, rng=api.RNG_PHILOX, seed=12, round_perms=8)
+    p1, _, c1, t1 = sc.scan_permute_rounds(obs, 60, G, save_clr=True, max_rounds=2, rng=api.RNG_PHILOX, seed=12,
+                                           round_perms=8)
+    assert t1 == 16 and int(p1["permute_n"].max()) == 16
+    p2, _, c2, t2 = sc.scan_permute_rounds(p1, 60, G, clr=c1, start_t=t1, max_rounds=3, rng=api.RNG_PHILOX, seed=12,
+                                           round_perms=8)
+    p3, _, c3, t3 = sc.scan_permute_rounds(p2, 60, G, clr=c2, start_t=t2, rng=api.RNG_PHILOX, seed=12, round_perms=8)
+    assert t2 == 40 and t3 == 61
+    for k in ("permute_p", "permute_n", "permute_finished"):
+        assert np.array_equal(p3[k], full[k]), k
+    assert np.array_equal(c3, clr_full)

@@ -24,17 +24,28 @@ struct PtS {          // one evaluated scan point, shared by the CTA
   double nsum;        // window null log-likelihood (scan-chromosome.c:92-94)
 };
 
-// init_scan_result, scan-chromosome.c:58-101 (window null sum is deferred)
+// init_scan_result, scan-chromosome.c:58-101 (window null sum is deferred).  Called by the 32 lanes
+// of one warp: the bisection of search_snppos becomes a 32-way search (4 dependent loads instead of
+// 17 for 200k sites); a sorted array has one answer whatever the probe sequence.
 __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
+  const int lane = threadIdx.x & 31;
   const int start = P.chr_start[chr], n = P.chr_nsnps[chr];
   const int *__restrict__ p = P.pos + start;
-  // search_snppos scan-chromosome.c:39-56
-  int i = 0, j = n;
+  // search_snppos scan-chromosome.c:39-56 ends with i = j - 1, j = first index >= 1 whose position
+  // is not below sweep_pos (n if none); index 0 is never probed there either
   const double sp = (double)pos;
-  while (j - i > 1) {
-    int m = (i + j) / 2;
-    if ((double)__ldg(p + m) < sp) i = m; else j = m;
+  int lo = 1, hi = n;                          // answer in [lo, hi]
+  while (hi > lo) {
+    const int span = hi - lo, step = (span + 31) / 32;
+    const int m = lo + lane * step;
+    const bool ge = m >= hi || !((double)__ldg(p + m) < sp);
+    const unsigned b = __ballot_sync(0xFFFFFFFFu, ge);      // monotone: 0..0 1..1
+    const int f = b ? __ffs(b) - 1 : 32;                     // first probe at or above the answer (32: none)
+    const int nhi = f < 32 ? min(lo + f * step, hi) : hi;
+    if (f > 0) lo = lo + (f - 1) * step + 1;
+    hi = nhi;
   }
+  const int j = min(lo, n), i = j - 1;
   int nearest;
   if (j == n) nearest = n - 1;
   else if ((sp - (double)__ldg(p + i)) < ((double)__ldg(p + j) - sp)) nearest = i;
@@ -51,9 +62,11 @@ __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
   } else if (nearest + er > chm_stop) {
     we = chm_stop; ws = chm_stop - er * 2; if (ws < chm_start) ws = chm_start;
   } else { ws = nearest - er; we = nearest + er; }
-  R.nearest = nearest; R.sweep_pos = pos; R.wstart = ws; R.wend = we;
-  int d = pos - __ldg(P.pos + nearest);
-  R.dnear = d < 0 ? -d : d;
+  if (lane == 0) {
+    R.nearest = nearest; R.sweep_pos = pos; R.wstart = ws; R.wend = we;
+    int d = pos - __ldg(P.pos + nearest);
+    R.dnear = d < 0 ? -d : d;
+  }
 }
 
 // record streams are read once per pass: keep them out of L1 so that the spline rows and the
@@ -380,9 +393,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     }
     __syncthreads();
     const int n_tl = W.n_list;
-    // window null sum from the complete tiles, in tile order (the cut tiles add their sites below)
-    if (WITHN && threadIdx.x == 0)
-      for (int t = t0; t <= t1; t++)
+    // window null sum from the complete tiles (the cut tiles add their sites below): the threads take
+    // one tile each, the fixed tree of the reduction below does the rest
+    if (WITHN)
+      for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads)
         if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
     // A warp owns chunks {warp, warp+8, ...} of every tile and walks them in batches of kB:
     // the kB records of the NEXT batch are fetched while the current one is evaluated,
@@ -576,7 +590,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   if (threadIdx.x == 0) W.bmF = 0;
   if (prune) {
     // bounds of the far tiles, once for every position the search of this cell can visit
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
       dev_init_point(P, t.chr, t.start_pos, A);
       dev_init_point(P, t.chr, (flags & kFlagSingle) ? t.start_pos : t.end_pos, B);
     }
@@ -587,7 +601,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   int pos = t.start_pos;
   for (int step = 0;; step++) {
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
-    if (threadIdx.x == 0) dev_init_point(P, t.chr, pos, M);
+    if (threadIdx.x < 32) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
     for (int exact = prune ? 0 : 1; exact < 2; exact++) {
       dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms);

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <limits>
 #include <string>
@@ -158,9 +159,14 @@ cudaError_t dev_malloc(T **p, size_t bytes) {
   return cudaStreamSynchronize(s);
 }
 
-// freed in the order of the stream that used the memory last
-void dev_free(void *p, cudaStream_t s) {
-  if (p) cudaFreeAsync(p, s);
+// `user` = the stream that used the memory last: waited for (idle in practice: the entry points
+// synchronise before they return), then the block goes back on the allocation stream, so the next
+// dev_malloc reuses it by plain stream order (a free on another stream is only reused
+// opportunistically, and a miss makes the pool map fresh memory: 30-130 ms per context measured)
+void dev_free(void *p, cudaStream_t user) {
+  if (!p) return;
+  cudaStreamSynchronize(user);
+  cudaFreeAsync(p, alloc_stream());
 }
 
 struct Ctx {
@@ -474,9 +480,9 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   if (p->eval_range < 1 || p->eval_range > 81920)
     return fail(FSCL_ERR_ARG, "eval_range must be in [1, 81920] (fscl.c:175)");
   CK(cudaSetDevice(p->device));
-  cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, p->device));
-  if (prop.major < 10) return fail(FSCL_ERR_NODEVICE, "device is not sm_100 class");
+  int cc_major = 0;      // one attribute, not cudaGetDeviceProperties: that call costs 10-200 ms per context
+  CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device));
+  if (cc_major < 10) return fail(FSCL_ERR_NODEVICE, "device is not sm_100 class");
   Ctx *c = new Ctx();
   c->device = p->device;
   c->n = p->n_snps; c->n_chr = p->n_chr; c->n_cls = p->n_cls;
@@ -493,6 +499,9 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   for (int i = c->n - 1; i >= 0; i--)
     c->chr_end_index[i] = (i == c->n - 1 || c->h_chr[i + 1] != c->h_chr[i]) ? i + 1 : c->chr_end_index[i + 1];
 
+  const bool timing = getenv("FSCL_B200_TIMING") != nullptr;
+  auto now_ms = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  const double tm0 = now_ms();
   std::vector<double> T(65536);
   if (p->log_table) memcpy(T.data(), p->log_table, sizeof(double) * 65536);
   else { T[0] = 0.0; for (int i = 1; i <= 0xFFFF; i++) T[i] = std::log((double)i); }   // sm-search.c:14-26
@@ -522,6 +531,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
     tlo[t] = lo; thi[t] = hi;
   }
 
+  const double tm1 = now_ms();
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -553,6 +563,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMemcpy(c->d_coefC, coefC.data(), sizeof(double) * coefC.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_logT, T.data(), sizeof(double) * 65536, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_null, p->null_tab, sizeof(double) * NC, cudaMemcpyHostToDevice));
+  const double tm2 = now_ms();
   upload_alpha_tables(A);
   CK(cudaGetLastError());
 
@@ -566,6 +577,9 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
+  if (timing)
+    fprintf(stderr, "fscl_create: host tables %.2f ms, stream + alloc + copies %.2f ms, constants + bucket %.2f ms\n", tm1 - tm0,
+            tm2 - tm1, now_ms() - tm2);
   *ctx_out = c;
   return FSCL_OK;
 }
@@ -775,7 +789,7 @@ static int device_begin(Ctx *c) {
   S.cur = 0;
   S.n_active = (int)act.size();
   // reserve the permutation slots once: rounds grow as cells are pruned, re-allocating on the way is slow
-  const size_t slot_bytes = (size_t)c->n * 16;
+  const size_t slot_bytes = (size_t)c->n * 20;        // tiles (key, pos, runs) + classes + scratch
   int want = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes));
   want = std::min(want, S.o.n_permute + 1);
   if (S.o.round_perms > 0) want = std::min(want, (S.o.round_perms + S.stride - 1) / S.stride);
@@ -791,10 +805,12 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
   if (n_active_out) *n_active_out = S.n_active;
   if (S.n_active == 0 || S.t_next > o.n_permute) return FSCL_OK;
   const size_t na = (size_t)S.n_active;
+  // at least 4 permutations per rank and round: the block draws and the swaps of ONE permutation are
+  // serial kernels (a thread / a CTA), so a round of one would leave the GPU idle behind them
   int R = o.round_perms > 0 ? o.round_perms
-                            : (int)std::min<size_t>(256, std::max<size_t>(S.stride, (16384 + na - 1) / na));
+                            : (int)std::min<size_t>(256, std::max<size_t>(4 * (size_t)S.stride, (16384 + na - 1) / na));
   R = (R + S.stride - 1) / S.stride * S.stride;
-  const size_t slot_bytes = (size_t)c->n * 16;
+  const size_t slot_bytes = (size_t)c->n * 20;
   const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);
   R = std::min(R, mem_cap * S.stride);
   R = std::min(R, o.n_permute - S.t_next + 1);

@@ -78,50 +78,16 @@ __device__ __forceinline__ int ld_stream(const int *p) {
 }
 
 // mid-range log-table entries (d >> 8) are touched about once per tile pass
-__device__ __forceinline__ double ld_lut_mid(const double *p) {
-#ifdef FSCL_LUT_NOALLOC
-  double v;
-  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
-  return v;
-#else
-  return __ldg(p);
-#endif
-}
+__device__ __forceinline__ double ld_lut_mid(const double *p) { return __ldg(p); }
 
 // 32-byte coefficient row in one 256-bit load (LDG.E.256)
 __device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, double &c2, double &c3) {
-#if !defined(FSCL_EXP)
   asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(p));
-#elif FSCL_EXP == 1     /* timing experiments only */
-  const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
-  c0 = a.x; c1 = a.y; c2 = b.x; c3 = b.y;
-#elif FSCL_EXP == 2
-  const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
-  c0 = a.x; c1 = a.y; c2 = 0.25; c3 = 0.125;
-#elif FSCL_EXP == 3
-  c0 = 1e-3; c1 = 2e-3; c2 = 0.25 + (double)(reinterpret_cast<size_t>(p) & 0xFF); c3 = 0.125;
-#endif
 }
 
-// GS alphas of one record, all inside the cut: rows issued back to back, then the FMAs.
-template <int GS>
-__device__ __forceinline__ void group_terms(double *acc, const double *la, double xq, const char *crow,
-                                            double inv_step, double offm) {
-  double x[GS], c0[GS], c1[GS], c2[GS], c3[GS];
-#pragma unroll
-  for (int v = 0; v < GS; v++) {
-    x[v] = xq + la[v];
-    // knot = trunc((x+20)/step): x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) rounds to the integer in
-    // the low word; a knot one off at a boundary is harmless (C2 spline)
-    const unsigned k = (unsigned)__double2loint(fma(x[v], inv_step, offm));
-    ld_row(reinterpret_cast<const double *>(crow + (unsigned long long)k * 32ull), c0[v], c1[v], c2[v], c3[v]);
-  }
-#pragma unroll
-  for (int v = 0; v < GS; v++) acc[v] += fma(x[v], fma(x[v], fma(x[v], c0[v], c1[v]), c2[v]), c3[v]);
-}
-
-// The common case (far tiles): the same GS <= 4 alphas for each of the KB records of a batch.
-// Two row buffers: the rows of record u+1 are in flight while record u is evaluated, so only the
+// GS <= 4 candidates, all inside the cut, for each of the KB records of a batch: the knot index is the
+// low word of x*inv_step + (20*inv_step - 0.5 + 2^52+2^51) (a knot one off at a boundary is harmless,
+// C2 spline).  Two row buffers: the rows of record u+1 are in flight while record u is evaluated, so only the
 // first load of a batch is exposed.
 template <int GS, int KB>
 __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double *la, const double (&x0)[KB],
@@ -179,9 +145,9 @@ struct PhaseScratch {
   int tile[kMaxTilesC];                 // per-tile classification
   int list[kMaxTilesC];                 // tiles that need a per-site walk, in order
   double tn[kMaxTilesC];                // per-tile null sums (WITHN)
-  unsigned kr[kMaxTilesC + 2][4];       // dev_cell_bounds: first knot | extra knots << 16 per candidate
+  unsigned kr[kMaxTilesC + 2][kNB];       // dev_cell_bounds: first knot | extra knots << 16 per candidate
   unsigned char jbF[kMaxTilesC + 2];    // cell level: leading candidates of the tile that a bound stands for
-  double ubF[4];                        // cell level: bound sums per candidate over those tiles
+  double ubF[kNB];                        // cell level: bound sums per candidate over those tiles
   int t0F, t1F, bmF;                    // tile range of the cell's windows; candidates with a bounded tile
   int n_list, bmask;
 };
@@ -220,7 +186,7 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
       const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
       bool open = true;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < kNB; j++) {
         const double la = c_alpha.la[kCoarse][j];
         const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), kclamp);
         const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), kclamp);
@@ -237,7 +203,9 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
   __syncthreads();
   // one warp per tile, lanes over its class runs; pmax = sparse table [level][first knot][class],
   // level l = maximum over knots k .. k+2^l-1: a range maximum is the larger of two entries
-  double ub[4] = {0.0, 0.0, 0.0, 0.0};
+  double ub[kNB];
+#pragma unroll
+  for (int j = 0; j < kNB; j++) ub[j] = 0.0;
   if (W.bmF) {
     const double *__restrict__ pm = P.pmax;
     const unsigned ncls = (unsigned)P.n_cls, l_stride = ((unsigned)P.n_knots + 2u) * ncls;
@@ -246,9 +214,9 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
       if (jb == 0) continue;
       const int nr = __ldg(tnrun + t);
       const int *__restrict__ rl = trun + (size_t)t * kTile;
-      const double *p1[4], *p2[4];
+      const double *p1[kNB], *p2[kNB];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
+      for (int j = 0; j < kNB; j++) {
         const unsigned kr = W.kr[t - t0][j], ka = kr & 0xFFFF, ex = kr >> 16;
         const unsigned lv = 31 - __clz(ex + 1);
         p1[j] = pm + ((size_t)lv * l_stride + (size_t)ka * ncls);
@@ -258,7 +226,7 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
         const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
         const double cntd = (double)(e >> 20);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < kNB; j++) {
           if (j >= jb) break;
           // fmax drops a NaN operand: tables with NaN pieces carry +inf here (host), never pruned
           ub[j] = fma(cntd, fmax(__ldg(p1[j] + cl), __ldg(p2[j] + cl)), ub[j]);
@@ -267,14 +235,14 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
     }
   }
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
+  for (int j = 0; j < kNB; j++) {
     double v = ub[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
     if (lane == 0) red[warp][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 4) {
+  if (threadIdx.x < kNB) {
     double v = 0.0;
 #pragma unroll
     for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
@@ -326,7 +294,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const int naw = jd;                 // candidates the tile walk (or a bound) accounts for
     // the cell-level bounds stand for their candidates' whole share of a tile: usable when none of
     // those candidates is summed directly (windows of at least a few thousand sites)
-    const bool bounds_on = WITHN && use_bound && W.bmF && jd >= min(na, 4);
+    const bool bounds_on = WITHN && use_bound && W.bmF && jd >= min(na, kNB);
     if (bounds_on && threadIdx.x == 0) W.bmask = W.bmF & ((1 << na) - 1);
     if (jd < na) {
       for (int i = iL + (int)threadIdx.x; i <= iR; i += kScanThreads) {
@@ -548,7 +516,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
     for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
     double s = (int)threadIdx.x < na ? (N + v) - N : 0.0;
-    if (WITHN && threadIdx.x < 4 && ((W.bmask >> threadIdx.x) & 1)) {
+    if (WITHN && threadIdx.x < kNB && ((W.bmask >> threadIdx.x) & 1)) {
       // bounded candidate: exact share of the walked tiles + bound of the others + tolerance for the
       // rounding of both (the terms are O(1e2), a window has < 2e5 of them)
       const double b = W.ubF[threadIdx.x];
@@ -616,7 +584,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         int best = -1; double bs = -1.7976931348623157e308;
         for (int j = 0; j < kCoarse; j++) if (!((bm >> j) & 1) && S[j] > bs) { bs = S[j]; best = j; }
         int redo = 0;
-        for (int j = 0; j < 4; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
+        for (int j = 0; j < kNB; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
         s_redo = redo;
         if (redo) atomicAdd(term_counter + 1, 1ull);
         M.clr = bs; M.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];

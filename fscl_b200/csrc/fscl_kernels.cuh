@@ -44,6 +44,10 @@ constexpr int kPermThreads = 1024;
 #ifndef FSCL_LIM_MID
 #define FSCL_LIM_MID 7
 #endif
+#ifndef FSCL_NB
+#define FSCL_NB 4
+#endif
+constexpr int kNB = FSCL_NB;     // leading coarse candidates a bound may stand for (dev_cell_bounds)
 constexpr int kLimLast = FSCL_LIM_LAST, kLimMid = FSCL_LIM_MID;   // extra knots a bound may span (dev_cell_bounds)
 #ifndef FSCL_DIRECT
 #define FSCL_DIRECT 128

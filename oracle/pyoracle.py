@@ -260,6 +260,7 @@ def lib():
             build()
         L = C.CDLL(ORACLE_SO)
         vp, ci, cd = C.c_void_p, C.c_int, C.c_double
+        L.fo_init_log_table.argtypes = [vp]
         L.fo_logt.restype = cd
         L.fo_logt.argtypes = [vp, ci]
         L.fo_dmax.argtypes = [vp, cd]

@@ -38,6 +38,21 @@ def problem(kind):
     if kind == "asc1":             # K=1 of M=20
         tab, opt = synth.config3(scale=0.05, depths=(100, 98, 96, 94, 90))
         return tab, po.RefProblem(tab, asc_depth=20, asc_min_freq=1).flatten(), opt["G"]
+    if kind == "invariant":        # --include-invariant: sites with count 0 / depth kept, their classes in the tables
+        rng = np.random.default_rng(9)
+        tab = synth.single_chromosome(6000, 3_000_000, 30, 12, planted=True)
+        inv = rng.random(6000) < 0.15
+        tab["count"][inv] = np.where(rng.random(int(inv.sum())) < 0.5, 0, 30)
+        return tab, po.RefProblem(tab, include_invariant=1).flatten(), 100_000
+    if kind == "folded":           # every site folded (minor allele counts), two depths
+        rng = np.random.default_rng(10)
+        tab = synth.single_chromosome(8000, 4_000_000, 40, 13, planted=True)
+        tab["depth"] = tab["depth"].copy()
+        tab["depth"][::3] = 36
+        tab["count"] = np.minimum(tab["count"], tab["depth"] - tab["count"]).astype(np.int32)
+        tab["count"] = np.maximum(tab["count"], 1).astype(np.int32)
+        tab["folded"] = np.ones(len(tab["pos"]), dtype=np.int32)      # (chr and folded share one zero array in synth)
+        return tab, po.RefProblem(tab).flatten(), 100_000
     if kind == "genome":           # c4 shape: 22 chromosomes, tiny scale
         tab, opt = synth.config4(scale=0.002)
         return tab, po.RefProblem(tab).flatten(), opt["G"]

@@ -20,7 +20,7 @@ def _oracle(flat, mode=2):
     return po.Oracle(flat, mode=mode)
 
 
-@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "asc1", "ascnan", "genome", "dense"])
+@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "asc1", "ascnan", "genome", "dense", "invariant", "folded"])
 def test_grid_eval_matches_oracle(api, kind):
     tab, flat, G = problem(kind)
     sc = api.Scanner(flat)
@@ -42,7 +42,7 @@ def test_grid_eval_matches_oracle(api, kind):
         assert abs(got[i]["null_logl"] - w["null_logl"]) <= 1e-12 * abs(w["null_logl"])
 
 
-@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "asc1", "ascnan", "genome", "dense"])
+@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "asc1", "ascnan", "genome", "dense", "invariant", "folded"])
 def test_scan_chromosome_matches_oracle(api, kind):
     tab, flat, G = problem(kind)
     sc = api.Scanner(flat)

@@ -99,10 +99,11 @@ def test_spline_eval_and_search_maxalpha_bit_exact(kind):
         assert w["clr"] == pt.clr or (np.isnan(w["clr"]) and np.isnan(pt.clr))
 
 
-@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "ascnan", "genome", "dense"])
+@pytest.mark.parametrize("kind", ["small50", "c1", "asc", "ascnan", "genome", "dense", "invariant", "folded"])
 def test_scan_chromosome_bit_exact_and_records(kind, tmp_path):
     tab, flat, G = problem(kind)
-    rp = po.RefProblem(tab, **({"asc_depth": 20, "asc_min_freq": 2} if kind.startswith("asc") else {}))
+    rp = po.RefProblem(tab, **({"asc_depth": 20, "asc_min_freq": 2} if kind.startswith("asc") else {}),
+                       **({"include_invariant": 1} if kind == "invariant" else {}))
     L = po.ref()
     L.scan_chromosome(rp.scan, rp.sm_p, 81920, 128, G, 1)
     s = rp.scan.contents

@@ -69,7 +69,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
-           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek"]
+           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters"]
 
 _lib = None
 
@@ -103,6 +103,7 @@ def load_library(path=LIB_PATH):
     L.fscl_bench_scan.argtypes = [vp, ci, ci, ci, vp, vp]
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_set_exact_candidates.argtypes = [vp, ci]
+    L.fscl_debug_counters.argtypes = [vp, vp]
     L.fscl_reset_stats.argtypes = [vp]
     L.fscl_fp64_peak.argtypes = [ci, vp]
     L.fscl_device_gen_blocks.argtypes = [vp, vp, ci, vp, ci, vp]

@@ -552,10 +552,10 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMemcpy(c->d_tile_hi, thi.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(dev_malloc(&c->d_logT, sizeof(double) * 65536));
   CK(dev_malloc(&c->d_null, sizeof(double) * NC));
-  CK(dev_malloc(&c->d_terms, 2 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
+  CK(dev_malloc(&c->d_terms, 16 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
   CK(dev_malloc(&c->d_chr_end, sizeof(int) * c->n));
   CK(cudaMemcpy(c->d_chr_end, c->chr_end_index.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
-  CK(cudaMemset(c->d_terms, 0, 2 * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_terms, 0, 16 * sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_chr_start, c->chr_start.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
@@ -1373,6 +1373,16 @@ extern "C" int fscl_project_pvalues(int n_pts, const fscl_pt_t *pts, const float
 }
 
 // --------------------------------------------------------------------------- bench / stats
+// debug builds (-DFSCL_TIMING, tools/probe_phases.py): slots 2..15 hold phase latencies summed over CTAs
+extern "C" int fscl_debug_counters(void *ctx, unsigned long long *out16) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !out16) return fail(FSCL_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out16, c->d_terms, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return FSCL_OK;
+}
+
 extern "C" int fscl_set_exact_candidates(void *ctx, int on) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(FSCL_ERR_ARG, "null context");

@@ -150,7 +150,16 @@ struct PhaseScratch {
   double ubF[kNB];                        // cell level: bound sums per candidate over those tiles
   int t0F, t1F, bmF;                    // tile range of the cell's windows; candidates with a bounded tile
   int n_list, bmask;
+#ifdef FSCL_TIMING
+  long long tacc[16], tlast;            // phase latencies seen by thread 0 (debug builds only)
+#endif
 };
+
+#ifdef FSCL_TIMING
+#define FSCL_TICK(W, slot) do { if (threadIdx.x == 0) { const long long now_ = clock64(); (W).tacc[slot] += now_ - (W).tlast; (W).tlast = now_; } } while (0)
+#else
+#define FSCL_TICK(W, slot) do { } while (0)
+#endif
 
 // Bounds of the far tiles for all grid-evals of one cell: sweep positions in [A.sweep_pos, B.sweep_pos],
 // windows between A's and B's (nearest site, window ends and the D3 shift are monotone in the position).
@@ -347,6 +356,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (jb << 20);
     }
     __syncthreads();
+    FSCL_TICK(W, (WITHN ? 2 : 7));
     // tiles that need the per-site walk, in order
     if (warp == 0) {
       int cnt = 0;
@@ -360,6 +370,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       if (lane == 0) W.n_list = cnt;
     }
     __syncthreads();
+    FSCL_TICK(W, (WITHN ? 3 : 8));
     const int n_tl = W.n_list;
     // window null sum from the complete tiles (the cut tiles add their sites below): the threads take
     // one tile each, the fixed tree of the reduction below does the rest
@@ -491,6 +502,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       }
     }
   }
+  FSCL_TICK(W, (WITHN ? 4 : 9));
   // fixed-tree reduction: deterministic, independent of launch shape
 #pragma unroll
   for (int j = 0; j < NA; j++) {
@@ -505,6 +517,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (lane == 0) red[warp][kMaxFine] = accn;
   }
   __syncthreads();
+  FSCL_TICK(W, (WITHN ? 5 : 10));
   if (threadIdx.x < NA) {
     double N = R.nsum;
     if (WITHN) {
@@ -527,6 +540,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
   }
   __syncthreads();
   if (WITHN && threadIdx.x == 0) R.nsum = S[kMaxFine];
+  FSCL_TICK(W, (WITHN ? 6 : 11));
 }
 
 
@@ -555,6 +569,9 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   const bool prune = !(flags & kFlagNoPrune);
   unsigned long long nterms = 0;
 
+#ifdef FSCL_TIMING
+  if (threadIdx.x == 0) { for (int q = 0; q < 16; q++) W.tacc[q] = 0; W.tlast = clock64(); }
+#endif
   if (threadIdx.x == 0) W.bmF = 0;
   if (prune) {
     // bounds of the far tiles, once for every position the search of this cell can visit
@@ -566,11 +583,13 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     dev_cell_bounds(P, trun, tnrun, A, B, red, W);
   }
   __syncthreads();
+  FSCL_TICK(W, 0);
   int pos = t.start_pos;
   for (int step = 0;; step++) {
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
     if (threadIdx.x < 32) dev_init_point(P, t.chr, pos, M);
     __syncthreads();
+    FSCL_TICK(W, 1);
     for (int exact = prune ? 0 : 1; exact < 2; exact++) {
       dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms);
       if (threadIdx.x == 0) {
@@ -591,6 +610,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         s_row = best < 0 ? kCoarse - 1 : best;
       }
       __syncthreads();
+      FSCL_TICK(W, 12);
       if (!s_redo) break;
     }
     const int row = s_row;
@@ -615,6 +635,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       s_next = next;
     }
     __syncthreads();
+    FSCL_TICK(W, 13);
     if (s_next < 0) break;
     pos = s_next;
   }
@@ -626,6 +647,10 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     out[blockIdx.x] = o;
     if (clr_matrix) clr_matrix[t.dst] = A.clr;
   }
+#ifdef FSCL_TIMING
+  if (threadIdx.x == 0)
+    for (int q = 0; q < 14; q++) atomicAdd(term_counter + 2 + q, (unsigned long long)W.tacc[q]);
+#endif
   if (COUNT) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nterms += __shfl_xor_sync(0xFFFFFFFFu, nterms, o);

@@ -183,6 +183,9 @@ int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_te
  * evaluated site by site -- the selected alpha, CLR and every later decision are unchanged.
  * on = 1 evaluates every candidate exactly (A/B tests, reference-equivalent term counts). */
 int fscl_set_exact_candidates(void *ctx, int on);
+/* Debug hook: the 16 device counters of the context ([0] SNP-terms of COUNT launches, [1] coarse passes
+ * repeated exactly; [2..15] phase latencies in cycles, only filled by a library built with -DFSCL_TIMING). */
+int fscl_debug_counters(void *ctx, unsigned long long *out16);
 int fscl_get_stats(void *ctx, fscl_stats_t *stats);
 int fscl_reset_stats(void *ctx);
 /* FP64 FMA peak of the device (dependent-chain microbenchmark), in TFLOP/s */

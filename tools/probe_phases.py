@@ -1,4 +1,10 @@
-"""Phase latencies per grid-eval seen by thread 0 of each CTA (library built with -DFSCL_TIMING)."""
+"""Phase latencies per grid-eval seen by thread 0 of each CTA.
+
+Needs a library built with -DFSCL_TIMING:
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DFSCL_TIMING \\
+       -o build/var/lib_timing.so fscl_b200/csrc/fscl_{kernels,host,tables}.cu
+  FSCL_B200_LIB=$PWD/build/var/lib_timing.so python tools/probe_phases.py
+"""
 import sys, ctypes as C, numpy as np
 sys.path.insert(0, '.')
 from fscl_b200 import api, synth
@@ -8,7 +14,6 @@ flat = po.RefProblem(tab).flatten()
 sc = api.Scanner(flat)
 sc.bench_scan(100000, 16)
 buf = (C.c_ulonglong * 16)()
-sc.L.fscl_debug_counters.argtypes = [C.c_void_p, C.c_void_p]
 sc.L.fscl_debug_counters(sc._ctx, buf)
 base = np.array(list(buf), dtype=np.float64)
 sc.bench_scan(100000, 16)

@@ -207,10 +207,10 @@ def main():
     sc.set_exact_candidates(False)
     fp64_peak = api.fp64_peak_tflops(local)
 
+    clocks = ClockSampler(local)          # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first sample
     run_rounds(max(args.warmup, 3))
     sc.reset_stats()
     barrier()
-    clocks = ClockSampler(local)
     t0 = time.perf_counter()
     pts, st = run_rounds(args.steps)
     barrier()

@@ -469,6 +469,8 @@ static void build_alpha_tables(const double *T, AlphaTables &A) {
   }
 }
 
+extern "C" void fscl_destroy(void *ctx);
+
 extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   if (!p || !ctx_out) return fail(FSCL_ERR_ARG, "null argument");
   *ctx_out = nullptr;
@@ -484,6 +486,10 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, p->device));
   if (cc_major < 10) return fail(FSCL_ERR_NODEVICE, "device is not sm_100 class");
   Ctx *c = new Ctx();
+  struct Guard {          // a failure below releases whatever the context already owns
+    Ctx *c;
+    ~Guard() { if (c) fscl_destroy(c); }
+  } guard{c};
   c->device = p->device;
   c->n = p->n_snps; c->n_chr = p->n_chr; c->n_cls = p->n_cls;
   c->h_chr.assign(p->chr, p->chr + c->n);
@@ -494,7 +500,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   c->chr_startpos.assign(p->chr_startpos, p->chr_startpos + c->n_chr);
   c->chr_bplen.assign(p->chr_bplen, p->chr_bplen + c->n_chr);
   for (int i = 0; i < c->n; i++)
-    if (c->h_cls[i] < 0 || c->h_cls[i] >= c->n_cls) { delete c; return fail(FSCL_ERR_ARG, "class index out of range"); }
+    if (c->h_cls[i] < 0 || c->h_cls[i] >= c->n_cls) { return fail(FSCL_ERR_ARG, "class index out of range"); }
   c->chr_end_index.resize(c->n);
   for (int i = c->n - 1; i >= 0; i--)
     c->chr_end_index[i] = (i == c->n - 1 || c->h_chr[i + 1] != c->h_chr[i]) ? i + 1 : c->chr_end_index[i + 1];
@@ -510,8 +516,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
 
   // class-major table [cls][knot][4] with the null model folded into c3
   const int K = p->n_knots, NC = p->n_cls;
-  if (NC >= (1 << 20)) { delete c; return fail(FSCL_ERR_ARG, "more than 2^20 classes"); }
-  if ((size_t)NC * (K + 2) * 32 >= ((size_t)1 << 32)) { delete c; return fail(FSCL_ERR_ARG, "spline table over 4 GiB"); }
+  if (NC >= (1 << 20)) { return fail(FSCL_ERR_ARG, "more than 2^20 classes"); }
+  if ((size_t)NC * (K + 2) * 32 >= ((size_t)1 << 32)) { return fail(FSCL_ERR_ARG, "spline table over 4 GiB"); }
   std::vector<double> coefC((size_t)(K + 2) * NC * 4);
   for (int cl = 0; cl < NC; cl++)
     for (int k = 0; k < K + 2; k++) {
@@ -580,6 +586,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   if (timing)
     fprintf(stderr, "fscl_create: host tables %.2f ms, stream + alloc + copies %.2f ms, constants + bucket %.2f ms\n", tm1 - tm0,
             tm2 - tm1, now_ms() - tm2);
+  guard.c = nullptr;
   *ctx_out = c;
   return FSCL_OK;
 }

@@ -168,3 +168,16 @@ def test_permutation_test_resumes_bit_exactly(api):
     for k in ("permute_p", "permute_n", "permute_finished"):
         assert np.array_equal(p3[k], full[k]), k
     assert np.array_equal(c3, clr_full)
+
+
+def test_create_rejects_bad_input_and_releases_the_context(api):
+    """Errors are return codes with a message; a context that fails half-way frees what it owns."""
+    tab, flat, G = problem("small50")
+    bad = dict(flat)
+    bad["cls"] = flat["cls"].copy()
+    bad["cls"][17] = len(flat["null_tab"]) + 3
+    for _ in range(3):
+        with pytest.raises(api.FsclError, match="class index out of range"):
+            api.Scanner(bad)
+    sc = api.Scanner(flat)                      # the library is still usable afterwards
+    assert len(sc.scan_chromosome(G)) > 0

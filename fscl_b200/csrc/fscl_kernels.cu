@@ -818,25 +818,32 @@ __device__ __forceinline__ int dev_philox_draw(unsigned long long seed, unsigned
   return (int)(c0 >> 1);
 }
 
-// Draw phase of snp_block_permute (scan-chromosome.c:345-363) for one permutation per thread
-// block (the block list is inherently sequential: i advances by the length just drawn).
+// Draw phase of snp_block_permute (scan-chromosome.c:345-363), one permutation per WARP.
+// The list is sequential only through `i` (each block starts where the previous one ended) and `i`
+// enters a block only through the end test `i + (k - j) >= n` (:361).  Block b always consumes draws
+// 2b and 2b+1 of the counter-based stream, so the 32 lanes draw and extend 32 blocks independently,
+// a prefix sum gives their start, and the first lane whose end test fires is redone with its true
+// `i` (the lanes behind it are discarded and drawn again in the next chunk).  Same list, same order
+// as the sequential loop (tests compare with the host generator block for block).
 // flags: 1 = D7 hit (defined behaviour, counted), 2 = a block length within rounding distance of
 // an integer (device log vs host log could truncate differently -> the host regenerates the
 // permutation), 4 = block list overflow (host regenerates).
-__global__ void gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ chr_end,
-                                  unsigned long long seed, const int *__restrict__ t_list, double nbp,
-                                  double width_bp, int4 *__restrict__ blocks, int stride,
-                                  int *__restrict__ counts, int *__restrict__ flags, int *__restrict__ d7) {
-  if (threadIdx.x != 0) return;
-  const int slot = blockIdx.x;
+__global__ void __launch_bounds__(32)
+gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ chr_end,
+                  unsigned long long seed, const int *__restrict__ t_list, double nbp,
+                  double width_bp, int4 *__restrict__ blocks, int stride,
+                  int *__restrict__ counts, int *__restrict__ flags, int *__restrict__ d7) {
+  const int slot = blockIdx.x, lane = threadIdx.x;
   const unsigned t = (unsigned)t_list[slot];
   int4 *out = blocks + (size_t)slot * stride;
-  unsigned ctr = 0;
+  const unsigned full = 0xFFFFFFFFu, below = (1u << lane) - 1u;
+  unsigned base = 0;                          // block index of lane 0
   int i = 0, nb = 0, flag = 0, nd7 = 0;
   while (i < n) {
-    int j = (int)(dev_philox_draw(seed, t, 0, ctr++) / (2147483647 + 1.0) * n);
-    const double len = -1.0 / nbp * log(dev_philox_draw(seed, t, 0, ctr++) / (2147483647 + 1.0));
-    if (len < 2147483647.0 && fabs(len - rint(len)) <= 1e-9 * fmax(len, 1.0)) flag |= 2;
+    const unsigned b = base + (unsigned)lane;
+    int j = (int)(dev_philox_draw(seed, t, 0, 2u * b) / (2147483647 + 1.0) * n);
+    const double len = -1.0 / nbp * log(dev_philox_draw(seed, t, 0, 2u * b + 1u) / (2147483647 + 1.0));
+    const int lflag = (len < 2147483647.0 && fabs(len - rint(len)) <= 1e-9 * fmax(len, 1.0)) ? 2 : 0;
     int k = j + (len < 2147483647.0 ? (int)len : 0x3FFFFFFF);
     if (k < n && k >= 0) {
       const int lim = chr_end[j];
@@ -850,17 +857,51 @@ __global__ void gen_blocks_kernel(int n, const int *__restrict__ pos, const int 
         k = lo;
       }
     }
-    if (i + (k - j) >= n) k = n;
-    if (k > n) { j = n - (k - j); k = n; nd7++; flag |= 1; }
-    const int L = min(k - j, n - i);
-    if (L > 0) {
-      if (nb < stride) out[nb] = make_int4(i, j, L, 0);
-      nb++;
-      i += L;
+    const int span = k - j;                   // what the end test adds to i
+    int jn = j, ld7 = 0;                      // the block if the end test does not fire
+    if (k > n) { jn = n - span; ld7 = 1; }
+    const int L0 = span > 0 ? span : 0;
+    int incl = L0;                            // inclusive prefix sum of the lengths
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(full, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int ib = i + incl - L0;             // start of this lane's block if no earlier end test fired
+    const bool ends = (long long)ib + (long long)span >= (long long)n;
+    const unsigned em = __ballot_sync(full, ends);
+    const int f = em ? __ffs(em) - 1 : 32;    // first lane whose end test fires
+    // lanes before f: final as drawn
+    const bool emit = lane < f && L0 > 0;
+    const unsigned mm = __ballot_sync(full, emit);
+    if (emit) {
+      const int q = nb + __popc(mm & below);
+      if (q < stride) out[q] = make_int4(ib, jn, L0, 0);
+    }
+    nb += __popc(mm);
+    const unsigned used = f < 32 ? ((2u << f) - 1u) : full;        // lanes whose draws are consumed now
+    flag |= __reduce_or_sync(full, ((used >> lane) & 1u) ? (unsigned)lflag : 0u);
+    nd7 += __popc(__ballot_sync(full, lane < f && ld7));
+    if (f < 32) {
+      // the block of lane f with its true i: the end test fires, so k = n and no D7 (:361-363)
+      const int i_f = __shfl_sync(full, ib, f), j_f = __shfl_sync(full, j, f);
+      const int L = min(n - j_f, n - i_f);
+      if (L > 0) {
+        if (lane == 0 && nb < stride) out[nb] = make_int4(i_f, j_f, L, 0);
+        nb++;
+      }
+      i = i_f + (L > 0 ? L : 0);
+      base += (unsigned)f + 1u;
+    } else {
+      i += __shfl_sync(full, incl, 31);
+      base += 32u;
     }
   }
-  if (nb > stride) flag |= 4;
-  counts[slot] = nb; flags[slot] = flag; d7[slot] = nd7;
+  if (lane == 0) {
+    if (nd7) flag |= 1;
+    if (nb > stride) flag |= 4;
+    counts[slot] = nb; flags[slot] = flag; d7[slot] = nd7;
+  }
 }
 
 void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,

@@ -270,11 +270,15 @@ def main():
 
     extra = {}
     if rank == 0 and not args.no_pruned_run:
-        # the configuration as quoted: 1000 permutations with stochastic 20-exceedance pruning
-        sc.reset_stats()
-        t0 = time.perf_counter()
-        p2, st2, _ = sc.scan_permute(obs, 1000, G, rng=api.RNG_PHILOX, seed=3, prune=1)
-        extra["pruned_run"] = {"n_permute": 1000, "seconds": time.perf_counter() - t0,
+        # the configuration as quoted: 1000 permutations with stochastic 20-exceedance pruning (twice: the
+        # first call also grows the permutation slots to the size a pruned test reserves)
+        runs = []
+        for _ in range(2):
+            sc.reset_stats()
+            t0 = time.perf_counter()
+            p2, st2, _ = sc.scan_permute(obs, 1000, G, rng=api.RNG_PHILOX, seed=3, prune=1)
+            runs.append(time.perf_counter() - t0)
+        extra["pruned_run"] = {"n_permute": 1000, "seconds": min(runs), "first_call_seconds": runs[0],
                                "scan_kernel_ms": st2["score_kernel_ms"], "other_kernels_ms": st2["permute_kernel_ms"],
                                "rounds": st2["n_rounds"],
                                "scan_equivalents": st2["n_tasks"] / n_cells,

@@ -771,6 +771,11 @@ static int ensure_small(Ctx *c, int n) {
   return FSCL_OK;
 }
 
+// permutations per rank and round at most: a round of few active cells is sized for 16384 searches, but 64
+// permuted genomes per launch already fill the GPU, cost a quarter of the memory of 256 and waste fewer
+// evaluations on cells that finish inside the round
+constexpr int kMaxRoundPerRank = 64;
+
 static int device_begin(Ctx *c) {
   PermState &S = c->perm;
   const int n = S.n_pts;
@@ -797,7 +802,7 @@ static int device_begin(Ctx *c) {
   S.n_active = (int)act.size();
   // reserve the permutation slots once: rounds grow as cells are pruned, re-allocating on the way is slow
   const size_t slot_bytes = (size_t)c->n * 20;        // tiles (key, pos, runs) + classes + scratch
-  int want = (int)std::min<size_t>(256, std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes));
+  int want = (int)std::min<size_t>(kMaxRoundPerRank, std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes));
   want = std::min(want, S.o.n_permute + 1);
   if (S.o.round_perms > 0) want = std::min(want, (S.o.round_perms + S.stride - 1) / S.stride);
   else want = (want + S.stride - 1) / S.stride;
@@ -815,7 +820,8 @@ static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out,
   // at least 4 permutations per rank and round: the block draws and the swaps of ONE permutation are
   // serial kernels (a thread / a CTA), so a round of one would leave the GPU idle behind them
   int R = o.round_perms > 0 ? o.round_perms
-                            : (int)std::min<size_t>(256, std::max<size_t>(4 * (size_t)S.stride, (16384 + na - 1) / na));
+                            : (int)std::min<size_t>((size_t)kMaxRoundPerRank * S.stride,
+                                                    std::max<size_t>(4 * (size_t)S.stride, (16384 + na - 1) / na));
   R = (R + S.stride - 1) / S.stride * S.stride;
   const size_t slot_bytes = (size_t)c->n * 20;
   const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);

@@ -7,4 +7,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.jso
 CMD="python bench.py --steps 1 --warmup 3 --round-perms 2 --no-cpu-baseline --no-pruned-run"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_cells -s 6 -c 1 -o gpurun_out/prof_scan_final -f $CMD > gpurun_out/ncu2.log 2>&1
-timeout 600 python tools/bench_c4.py --perms 200 --slots 4 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json
+timeout 600 python tools/bench_genome.py --perms 200 --slots 4 > gpurun_out/bench_c4.json 2> gpurun_out/bench_c4.err; cat gpurun_out/bench_c4.json

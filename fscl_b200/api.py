@@ -69,7 +69,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
-           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters"]
+           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima"]
 
 _lib = None
 
@@ -108,6 +108,7 @@ def load_library(path=LIB_PATH):
     L.fscl_fp64_peak.argtypes = [ci, vp]
     L.fscl_device_gen_blocks.argtypes = [vp, vp, ci, vp, ci, vp]
     L.fscl_host_alpha_tables.argtypes = [vp, vp, vp, vp]
+    L.fscl_host_piece_maxima.argtypes = [ci, ci, C.c_double, vp, vp, vp, C.c_int64, vp]
     L.fscl_host_enum_cells.argtypes = [ci, vp, vp, ci, vp, vp, vp, ci]
     L.fscl_host_gen_blocks.argtypes = [ci, vp, vp, vp, ci, vp, ci, vp]
     L.fscl_host_replay_round.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp]
@@ -144,6 +145,19 @@ def host_alpha_tables(log_table=None):
     _check(L.fscl_host_alpha_tables(None if lt is None else lt.ctypes.data, la.ctypes.data, dmax.ctypes.data,
                                     n.ctypes.data))
     return la, dmax, n
+
+
+def host_piece_maxima(coef, null_tab, step):
+    """[levels][n_knots+2][n_cls] upper bounds of (spline - null) over knot ranges (fscl_b200.h)."""
+    L = load_library()
+    coef = np.ascontiguousarray(coef, dtype=np.float64)
+    null_tab = np.ascontiguousarray(null_tab, dtype=np.float64)
+    n_cls, K = coef.shape[0], coef.shape[1]
+    out = np.zeros(12 * (K + 2) * n_cls, dtype=np.float64)
+    lv = C.c_int32(0)
+    _check(L.fscl_host_piece_maxima(n_cls, K, float(step), coef.ctypes.data, null_tab.ctypes.data, out.ctypes.data,
+                                    out.size, C.byref(lv)))
+    return out[:lv.value * (K + 2) * n_cls].reshape(lv.value, K + 2, n_cls)
 
 
 def host_enum_cells(chr_startpos, chr_bplen, G):

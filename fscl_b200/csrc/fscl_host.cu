@@ -1227,6 +1227,26 @@ extern "C" int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *o, i
 // --------------------------------------------------------------------------- host-only entry points
 // These run without a device (tests exercise them on CPU-only machines); they are
 // the same code the GPU path uses for its host side.
+// The range-maximum table of the candidate bounds, as fscl_create builds it (host only; test hook):
+// coef = [n_cls][n_knots][4], null_tab = [n_cls]; out = [levels][n_knots+2][n_cls], *levels_out = levels.
+extern "C" int fscl_host_piece_maxima(int n_cls, int n_knots, double step, const double *coef, const double *null_tab,
+                                      double *out, int64_t cap, int32_t *levels_out) {
+  if (!coef || !null_tab || !out || !levels_out || n_cls <= 0 || n_knots <= 0) return fail(FSCL_ERR_ARG, "bad argument");
+  const int K = n_knots;
+  std::vector<double> coefC((size_t)(K + 2) * n_cls * 4), ptab;
+  for (int cl = 0; cl < n_cls; cl++)
+    for (int k = 0; k < K + 2; k++) {
+      const double *q = coef + ((size_t)cl * K + std::min(k, K - 1)) * 4;
+      double *d = coefC.data() + ((size_t)cl * (K + 2) + k) * 4;
+      d[0] = q[0]; d[1] = q[1]; d[2] = q[2]; d[3] = q[3] - null_tab[cl];
+    }
+  build_piece_maxima(coefC.data(), n_cls, K, step, ptab);
+  if ((int64_t)ptab.size() > cap) return fail(FSCL_ERR_ARG, "output too small");
+  memcpy(out, ptab.data(), sizeof(double) * ptab.size());
+  *levels_out = (int32_t)(ptab.size() / ((size_t)(K + 2) * n_cls));
+  return FSCL_OK;
+}
+
 extern "C" int fscl_host_alpha_tables(const double *log_table, double *la, int32_t *dmax, int32_t *n) {
   if (!la || !dmax || !n) return fail(FSCL_ERR_ARG, "bad argument");
   std::vector<double> T(65536);

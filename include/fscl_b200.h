@@ -151,6 +151,10 @@ int fscl_perm_seek(void *ctx, int32_t t_next);
  * sm-search.c:276-296, with the per-alpha distance cut), cell enumeration, the
  * draw phase of snp_block_permute, one round of counting/pruning, RNG draws. */
 int fscl_host_alpha_tables(const double *log_table, double *la, int32_t *dmax, int32_t *n);
+/* The range-maximum table behind the candidate bounds, as fscl_create builds it: out =
+ * [levels][n_knots+2][n_cls], entry [l][k][c] >= spline_c(x) - null_c for every x whose knot index is in k .. k+2^l-1. */
+int fscl_host_piece_maxima(int n_cls, int n_knots, double step, const double *coef, const double *null_tab,
+                           double *out, int64_t cap, int32_t *levels_out);
 int fscl_host_enum_cells(int n_chr, const int32_t *chr_startpos, const int32_t *chr_bplen, int large_grid_sp,
                          int32_t *cell_chr, int32_t *cell_start, int32_t *cell_end, int cap);
 int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, const fscl_permute_opts_t *opts,

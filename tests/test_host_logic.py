@@ -166,3 +166,34 @@ def test_sharded_rounds_over_gloo_two_ranks(api, tmp_path):
     pts0, _ = o.scan(opt["G"])
     want, _, _, _, _ = o.scan_permute(pts0, 30, opt["G"], o.rng("philox", 5))
     assert np.array_equal(a[0], want["permute_p"]) and np.array_equal(a[1], want["permute_n"])
+
+
+@pytest.mark.parametrize("kind", ["small50", "asc", "ascnan"])
+def test_piece_maxima_bound_every_spline_value(api, kind):
+    """The candidate bounds rest on pmax[l][k][c] >= spline_c(x) - null_c for every x of the knots k .. k+2^l-1
+    (host-built table): checked on a dense sample of x for every class and knot; pieces with
+    non-finite coefficients must bound to +inf."""
+    from tests.common import problem
+    tab, flat, G = problem(kind)
+    coef, null_tab, step, K = flat["coef"], flat["null_tab"], flat["step"], flat["n_knots"]
+    P = api.host_piece_maxima(coef, null_tab, step)
+    n_cls = coef.shape[0]
+    assert P.shape[1:] == (K + 2, n_cls) and P.shape[0] >= 8
+    fin = np.isfinite(coef).all(axis=2) & np.isfinite(null_tab)[:, None]          # [cls][knot]
+    xs = np.linspace(0.0, 1.0, 41)
+    with np.errstate(all="ignore"):
+        for k in range(K + 2):
+            kk = min(k, K - 1)                                                       # rows K, K+1 repeat piece K-1
+            x = -20.0 + (k + xs) * step
+            c = coef[:, kk, :]
+            c3 = c[:, 3:4] - null_tab[:, None]                                       # the device table folds the null into c3
+            y = x[None, :] * (x[None, :] * (x[None, :] * c[:, 0:1] + c[:, 1:2]) + c[:, 2:3]) + c3
+            ok = fin[:, kk]
+            assert (P[0, k, ok][:, None] >= y[ok]).all(), (kind, k)
+            assert np.isposinf(P[0, k, ~ok]).all(), (kind, k)
+        # level l = running maximum over 2^l consecutive knots (clipped at the last row)
+        for l in range(1, P.shape[0]):
+            w = 1 << l
+            for k in (0, 7, K // 2, K - 3, K + 1):
+                want = P[0, k:min(k + w, K + 2), :].max(axis=0)
+                assert np.array_equal(P[l, k, :], want), (kind, l, k)

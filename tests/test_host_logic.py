@@ -197,3 +197,49 @@ def test_piece_maxima_bound_every_spline_value(api, kind):
             for k in (0, 7, K // 2, K - 3, K + 1):
                 want = P[0, k:min(k + w, K + 2), :].max(axis=0)
                 assert np.array_equal(P[l, k, :], want), (kind, l, k)
+
+
+def test_tile_bounds_dominate_exact_tile_sums(api):
+    """The inequality behind the pruning, end to end on the CPU: for tiles wholly inside a
+    candidate's cut, sum over class runs of count * (range maximum over the knots the tile spans) >= the
+    exact sum of the tile's terms, for random sweep positions of a c2-shaped problem."""
+    from tests.common import problem
+    from oracle import pyoracle as po
+    tab, flat, G = problem("mid100")
+    pos, cls = flat["pos"].astype(np.int64), flat["cls"]
+    coef, null_tab, step, K = flat["coef"], flat["null_tab"], flat["step"], flat["n_knots"]
+    P = api.host_piece_maxima(coef, null_tab, step)[0]                 # [K+2][n_cls]
+    la_tab, dmax_tab, n_tab = api.host_alpha_tables()
+    la, dmax = la_tab[11][:4], dmax_tab[11][:4]                        # the four widest coarse candidates
+    LT = po.log_table()
+
+    def logt(d):
+        sh = np.where(d > 0xFFFFFF, 16, np.where(d > 0xFFFF, 8, 0))
+        c = np.where(d > 0xFFFFFF, 11.783502069519070, np.where(d > 0xFFFF, 5.545177444479562, 0.0))
+        return np.where(sh > 0, c + LT[d >> sh], LT[d >> sh])
+
+    rng = np.random.default_rng(4)
+    T, n, checked = 1024, len(pos), 0
+    for sweep in rng.integers(pos[0], pos[-1], 12):
+        d = np.abs(pos - sweep)
+        x0 = logt(d)
+        for t in range(n // T):
+            lo, hi = t * T, t * T + T
+            if pos[lo] <= sweep <= pos[hi - 1]:
+                continue                                                # two-sided tile: not a far tile
+            dfar, dnr = int(d[lo:hi].max()), int(d[lo:hi].min())
+            cnt = np.bincount(cls[lo:hi], minlength=len(null_tab))
+            nz = np.nonzero(cnt)[0]
+            for j in range(4):
+                if dmax[j] < dfar:
+                    continue                                            # the cut does not cover the tile
+                x = x0[lo:hi] + la[j]
+                k = np.clip(((x + 20.0) / step).astype(np.int64), 0, K - 1)
+                c = coef[cls[lo:hi], k]
+                exact = float(np.sum(x * (x * (x * c[:, 0] + c[:, 1]) + c[:, 2]) + (c[:, 3] - null_tab[cls[lo:hi]])))
+                ka = int(np.clip((logt(np.array([dnr]))[0] + la[j] + 20.0) / step, 0, K + 1))
+                kb = int(np.clip((logt(np.array([dfar]))[0] + la[j] + 20.0) / step, 0, K + 1))
+                ub = float(np.sum(cnt[nz] * P[max(ka - 1, 0):kb + 2][:, nz].max(axis=0)))   # +-1 knot: device knot map vs this one
+                assert ub >= exact - 1e-9 * (1.0 + abs(exact)), (int(sweep), t, j, ub, exact)
+                checked += 1
+    assert checked > 300

@@ -43,7 +43,7 @@ class fscl_permute_opts_t(C.Structure):
     _fields_ = [("n_permute", C.c_int32), ("permute_nbp", C.c_double), ("large_grid_sp", C.c_int32),
                 ("scan_width_mb", C.c_double), ("rng_kind", C.c_int32), ("seed", C.c_uint64),
                 ("prune", C.c_int32), ("first_perm", C.c_int32), ("perm_stride", C.c_int32),
-                ("round_perms", C.c_int32)]
+                ("round_perms", C.c_int32), ("save_clr", C.c_int32)]
 
 
 class fscl_stats_t(C.Structure):
@@ -69,7 +69,9 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_perm_end", "fscl_bench_scan", "fscl_get_stats", "fscl_reset_stats", "fscl_fp64_peak", "fscl_device_gen_blocks",
            "fscl_host_alpha_tables", "fscl_host_enum_cells", "fscl_host_gen_blocks", "fscl_host_replay_round",
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
-           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima"]
+           "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima",
+           "fscl_perm_fetch_clr", "fscl_perm_project", "fscl_comm_unique_id", "fscl_comm_init_rank", "fscl_comm_init_all",
+           "fscl_comm_destroy", "fscl_comm_info"]
 
 _lib = None
 
@@ -116,6 +118,13 @@ def load_library(path=LIB_PATH):
     L.fscl_project_pvalues.argtypes = [ci, vp, vp, C.c_double, vp, vp]
     L.fscl_ncx2_sf.argtypes = [ci, vp, C.c_double, vp, vp]
     L.fscl_build_tables.argtypes = [ci, ci, vp, vp, ci, ci, ci, ci, ci, vp, vp, vp]
+    L.fscl_perm_fetch_clr.argtypes = [vp, vp, vp, C.c_int64]
+    L.fscl_perm_project.argtypes = [vp, C.c_double, vp, vp]
+    L.fscl_comm_unique_id.argtypes = [vp]
+    L.fscl_comm_init_rank.argtypes = [vp, ci, ci, vp]
+    L.fscl_comm_init_all.argtypes = [vp, ci]
+    L.fscl_comm_destroy.argtypes = [vp]
+    L.fscl_comm_info.argtypes = [vp, vp, vp]
     _lib = L
     return L
 
@@ -123,6 +132,14 @@ def load_library(path=LIB_PATH):
 def _check(rc):
     if rc != 0:
         raise FsclError(f"fscl_b200 error {rc}: {_lib.fscl_last_error().decode()}")
+
+
+def comm_unique_id():
+    """128 opaque bytes naming a new communicator (ncclGetUniqueId); make on one rank, ship to all."""
+    L = load_library()
+    buf = (C.c_char * 128)()
+    _check(L.fscl_comm_unique_id(buf))
+    return bytes(buf.raw)
 
 
 def fp64_peak_tflops(device=0):
@@ -176,7 +193,7 @@ def host_gen_blocks(chr_, pos, t, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DE
     """(i, j, len) triples of permutation t (draw phase of snp_block_permute) and the D7 count."""
     L = load_library()
     chr_, pos = _i32(chr_), _i32(pos)
-    o = fscl_permute_opts_t(0, nbp, 1, width_mb, rng, seed, 1, 0, 1, 0)
+    o = fscl_permute_opts_t(0, nbp, 1, width_mb, rng, seed, 1, 0, 1, 0, 0)
     blocks = np.zeros((max_blocks, 3), dtype=np.int32)
     d7 = C.c_int32(0)
     nb = L.fscl_host_gen_blocks(len(pos), chr_.ctypes.data, pos.ctypes.data, C.byref(o), t, blocks.ctypes.data,
@@ -191,7 +208,7 @@ def host_replay_round(pts, active, matrix, t_first, seed=DEFAULT_SEED, prune=1, 
     L = load_library()
     active = _i32(active)
     matrix = np.ascontiguousarray(matrix, dtype=np.float64)
-    o = fscl_permute_opts_t(0, 0.1, 1, 1.0, RNG_PHILOX, seed, prune, 0, 1, 0)
+    o = fscl_permute_opts_t(0, 0.1, 1, 1.0, RNG_PHILOX, seed, prune, 0, 1, 0, 0)
     r = L.fscl_host_replay_round(pts.ctypes.data, active.ctypes.data, len(active), matrix.ctypes.data,
                                  matrix.shape[0], t_first, C.byref(o),
                                  None if permute_clr is None else permute_clr.ctypes.data)
@@ -314,9 +331,9 @@ class Scanner:
     # ---- permutations -----------------------------------------------------
     @staticmethod
     def permute_opts(n_permute, G, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DEFAULT_SEED, prune=1,
-                     first_perm=0, perm_stride=1, round_perms=0):
+                     first_perm=0, perm_stride=1, round_perms=0, keep_clr=0):
         return fscl_permute_opts_t(n_permute, nbp, G, width_mb, rng, seed, prune, first_perm, perm_stride,
-                                   round_perms)
+                                   round_perms, keep_clr)
 
     def block_permute(self, t, nbp=0.1, width_mb=1.0, rng=RNG_PHILOX, seed=DEFAULT_SEED, max_blocks=1 << 16):
         o = self.permute_opts(0, 1, nbp, width_mb, rng, seed)
@@ -401,6 +418,36 @@ class Scanner:
         _check(self.L.fscl_perm_end(self._ctx, C.byref(st)))
         return pts, st.asdict(), clr
 
+    # ---- multi-GPU ----------------------------------------------------------
+    def comm_init_rank(self, world, rank, unique_id):
+        """Join a communicator of ``world`` contexts, one process per GPU.  ``unique_id`` = the 128 bytes
+        of ``comm_unique_id()`` made on rank 0 and shipped to every rank.  From then on
+        ``scan_chromosome`` shards over cells and ``scan_permute`` over permutations (NCCL all-gather per
+        round inside the library); every rank must make the same calls and gets identical results."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        _check(self.L.fscl_comm_init_rank(self._ctx, world, rank, buf))
+
+    def comm_info(self):
+        w, r = C.c_int(1), C.c_int(0)
+        _check(self.L.fscl_comm_info(self._ctx, C.byref(w), C.byref(r)))
+        return w.value, r.value
+
+    # ---- stored permuted CLRs / projection, device-resident -------------------
+    def fetch_clr(self, n_pts):
+        """(offsets[n_pts+1], packed float32): the stored permuted CLRs of the last test run with
+        ``save_clr`` / ``keep_clr`` -- cell i is packed[offsets[i]:offsets[i+1]] (one gather + one copy)."""
+        off = np.zeros(n_pts + 1, dtype=np.int64)
+        _check(self.L.fscl_perm_fetch_clr(self._ctx, off.ctypes.data, None, 0))
+        packed = np.zeros(max(int(off[-1]), 1), dtype=np.float32)
+        _check(self.L.fscl_perm_fetch_clr(self._ctx, off.ctypes.data, packed.ctypes.data, packed.size))
+        return off, packed[:int(off[-1])]
+
+    def project(self, n_pts, df=2.0):
+        """Projected p-values computed on the device from the CLRs kept there: (lambda_hat, p)."""
+        lam, p = np.zeros(n_pts), np.zeros(n_pts)
+        _check(self.L.fscl_perm_project(self._ctx, float(df), lam.ctypes.data, p.ctypes.data))
+        return lam, p
+
     # ---- measurement --------------------------------------------------------
     def bench_scan(self, G, n_perm_slots, count_terms=False):
         terms = C.c_int64(0)
@@ -428,8 +475,6 @@ class Scanner:
 
 def _c_fmt_e(v):
     """printf("%1.3e")"""
-    if v == 0 or not math.isfinite(v):
-        return "%1.3e" % v
     return "%1.3e" % v
 
 

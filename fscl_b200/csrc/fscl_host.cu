@@ -9,6 +9,9 @@
 #include "../../include/fscl_b200.h"
 #include "fscl_kernels.cuh"
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -17,6 +20,7 @@
 #include <ctime>
 #include <functional>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -127,26 +131,40 @@ struct PermState {
   int t_next = 0, R = 0;
   // device-resident rounds (Philox): counters, active list and pruning stay on the GPU
   bool on_device = false;
-  int n_active = 0, cur = 0;           // d_active[cur] holds the active list
+  int n_active = 0, cur = 0;           // d_active[cur] / d_count[cur] hold the active list and its length
+  // pipelined engine: the host runs about one round ahead of the GPU and learns the active count two rounds late
+  long round = 0, collected = 0;       // rounds enqueued so far; rounds whose timings the host has read
+  int64_t rounds_at_begin = 0;
+  int na_round = 0, ns_round = 0;      // launch bound (stale active count) and local permutations of the round in flight
+  size_t chunk = 0;                    // doubles per rank in the gathered matrix of the round in flight
+  int clr_cap = 0;                     // stored permuted CLRs per cell on the device: min(n_permute + 1, FSCL_NULL_SAVE)
+  bool keep_clr = false;
 };
 
 // Device memory comes from the stream-ordered pool of the device with an unlimited release
 // threshold: creating and destroying a context (one per end-to-end call of the Python layer)
 // reuses cached blocks instead of paying cudaMalloc / cudaFree (device-wide synchronisation, tens
 // of ms each once other libraries hold mappings).  Callers free only memory no stream still uses.
-cudaStream_t g_alloc_stream[64] = {};
+constexpr int kMaxDevices = 64;
+cudaStream_t g_alloc_stream[kMaxDevices] = {};
+std::mutex g_alloc_lock;
 
+// FSCL_B200_POOL_KEEP_MB: how much freed memory the device's pool keeps cached (default: all of it; 0 gives
+// every block back to the driver as soon as it is free).
 cudaStream_t alloc_stream() {
   int dev = 0;
-  cudaGetDevice(&dev);
-  dev &= 63;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;   // null stream: still correct
+  std::lock_guard<std::mutex> guard(g_alloc_lock);
   if (!g_alloc_stream[dev]) {
-    cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking);
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
       unsigned long long keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-    }
+      if (const char *mb = getenv("FSCL_B200_POOL_KEEP_MB")) keep = strtoull(mb, nullptr, 10) << 20;
+      if (cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
+    } else cudaGetLastError();
+    g_alloc_stream[dev] = s;
   }
   return g_alloc_stream[dev];
 }
@@ -195,7 +213,7 @@ struct Ctx {
   int *d_pp = nullptr, *d_pn = nullptr, *d_pf = nullptr;
   double *d_pt_clr = nullptr;
   float *d_pclr = nullptr;
-  int pts_cap = 0; bool pclr_alloc = false;
+  int pts_cap = 0; size_t pclr_floats = 0;
   int *d_small = nullptr;                          // [5 * kSmall]: t_list, rows, flags, d7, scored ; + count
   int small_cap = 0;
   Task *d_tasks = nullptr; OutPt *d_out = nullptr; size_t tasks_cap = 0;
@@ -203,9 +221,35 @@ struct Ctx {
   std::vector<Task> h_tasks;
   std::vector<OutPt> h_out;
   double *d_matrix = nullptr; size_t matrix_cap = 0;
+  // second permutation slot set + what the pipelined rounds need (see device_round_score)
+  TileSet ts1{};
+  int *d_pcls1 = nullptr, *d_scratch1 = nullptr, *d_blkoff1 = nullptr, *d_blkcnt1 = nullptr;
+  int4 *d_blocks1 = nullptr; size_t blocks_cap1 = 0; int max_slots1 = 0;
+  cudaStream_t prep = nullptr;                    // block draws, swaps and bucketing of the NEXT round
+  cudaEvent_t ev_gen[2] = {}, ev_prep[2] = {}, ev_scan[2] = {};                                 // per slot set
+  bool set_used[2] = {false, false};
+  cudaEvent_t ev_round[4] = {}, ev_k0[4] = {}, ev_k1[4] = {};                                   // ring by round
+  int *h_pin = nullptr;                           // pinned: [4] counts, then per set [3 * kPinSlots] flags / d7 / block counts
+  int *d_eng = nullptr;                           // [2] active counts, [1] task count of the round, then per set t_list/flags/d7
+  int *d_scored = nullptr; int scored_cap = 0;
+  unsigned long long *d_totals = nullptr;         // [0] searches launched, [1] permutations scored
+  long long *d_off = nullptr; float *d_pack = nullptr; size_t pack_cap = 0; int off_cap = 0;
+  // multi-GPU: NCCL communicator (one rank per context)
+  ncclComm_t comm = nullptr;
+  int world = 1, rank = 0;
   PermState perm;
   fscl_stats_t stats{};
 };
+
+constexpr int kPinSlots = 1024;                    // permutations per rank and round the pinned flag area holds
+
+struct SlotRef {
+  TileSet &ts; int *&pcls; int *&scratch; int4 *&blocks; size_t &blocks_cap; int *&blkoff; int *&blkcnt; int &max_slots;
+};
+SlotRef slot_set(Ctx *c, int k) {
+  if (k == 0) return SlotRef{c->ts, c->d_pcls, c->d_scratch, c->d_blocks, c->blocks_cap, c->d_blkoff, c->d_blkcnt, c->max_slots};
+  return SlotRef{c->ts1, c->d_pcls1, c->d_scratch1, c->d_blocks1, c->blocks_cap1, c->d_blkoff1, c->d_blkcnt1, c->max_slots1};
+}
 
 int ensure_tasks(Ctx *c, size_t n) {
   if (n <= c->tasks_cap) return FSCL_OK;
@@ -287,22 +331,25 @@ int alloc_tiles(TileSet &t, int slots, int n_pad) {
   return FSCL_OK;
 }
 
-int ensure_slots(Ctx *c, int slots) {
-  if (slots <= c->max_slots) return FSCL_OK;
-  if (c->d_pcls) dev_free(c->d_pcls, c->stream);
-  if (c->d_scratch) dev_free(c->d_scratch, c->stream);
-  if (c->d_blkoff) dev_free(c->d_blkoff, c->stream);
-  if (c->d_blkcnt) dev_free(c->d_blkcnt, c->stream);
-  c->d_blkcnt = nullptr;
-  free_tiles(c->ts, c->stream);
-  c->d_pcls = c->d_scratch = c->d_blkoff = nullptr; c->max_slots = 0;
-  { int rc = alloc_tiles(c->ts, slots, c->n_pad); if (rc) return rc; }
-  CK(dev_malloc(&c->d_pcls, (size_t)slots * c->n * sizeof(int)));
-  c->ts.cls = c->d_pcls; c->ts.cls_stride = (size_t)c->n;
-  CK(dev_malloc(&c->d_scratch, (size_t)slots * c->n * sizeof(int)));
-  CK(dev_malloc(&c->d_blkoff, (size_t)(slots + 1) * sizeof(int)));
-  CK(dev_malloc(&c->d_blkcnt, (size_t)(slots + 1) * sizeof(int)));
-  c->max_slots = slots;
+int ensure_slots(Ctx *c, int slots, int set = 0) {
+  SlotRef Q = slot_set(c, set);
+  if (slots <= Q.max_slots) return FSCL_OK;
+  // growing a set that kernels may still read: wait for both streams first (rare: sets are sized at begin)
+  if (c->prep) CK(cudaStreamSynchronize(c->prep));
+  if (Q.pcls) dev_free(Q.pcls, c->stream);
+  if (Q.scratch) dev_free(Q.scratch, c->stream);
+  if (Q.blkoff) dev_free(Q.blkoff, c->stream);
+  if (Q.blkcnt) dev_free(Q.blkcnt, c->stream);
+  Q.blkcnt = nullptr;
+  free_tiles(Q.ts, c->stream);
+  Q.pcls = Q.scratch = Q.blkoff = nullptr; Q.max_slots = 0;
+  { int rc = alloc_tiles(Q.ts, slots, c->n_pad); if (rc) return rc; }
+  CK(dev_malloc(&Q.pcls, (size_t)slots * c->n * sizeof(int)));
+  Q.ts.cls = Q.pcls; Q.ts.cls_stride = (size_t)c->n;
+  CK(dev_malloc(&Q.scratch, (size_t)slots * c->n * sizeof(int)));
+  CK(dev_malloc(&Q.blkoff, (size_t)(slots + 1) * sizeof(int)));
+  CK(dev_malloc(&Q.blkcnt, (size_t)(slots + 1) * sizeof(int)));
+  Q.max_slots = slots;
   return FSCL_OK;
 }
 
@@ -432,6 +479,60 @@ struct BlockGen {
 };
 
 }  // namespace
+
+// NCCL, resolved at run time (see the multi-GPU section below)
+namespace {
+struct NcclApi {
+  void *h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+} g_nccl;
+std::mutex g_nccl_lock;
+
+int nccl_load() {
+  std::lock_guard<std::mutex> guard(g_nccl_lock);
+  if (g_nccl.h) return FSCL_OK;
+  void *h = nullptr;
+  if (const char *path = getenv("FSCL_B200_NCCL")) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(FSCL_ERR_ARG, std::string("cannot load libnccl.so.2: ") + dlerror());
+#define FSCL_SYM(field, name)                                                                        \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                                        \
+  if (!g_nccl.field) { dlclose(h); return fail(FSCL_ERR_ARG, std::string("libnccl lacks ") + name); }
+  FSCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  FSCL_SYM(CommInitRank, "ncclCommInitRank")
+  FSCL_SYM(CommInitAll, "ncclCommInitAll")
+  FSCL_SYM(CommDestroy, "ncclCommDestroy")
+  FSCL_SYM(AllGather, "ncclAllGather")
+  FSCL_SYM(GetErrorString, "ncclGetErrorString")
+  FSCL_SYM(GroupStart, "ncclGroupStart")
+  FSCL_SYM(GroupEnd, "ncclGroupEnd")
+#undef FSCL_SYM
+  g_nccl.h = h;
+  return FSCL_OK;
+}
+}  // namespace
+
+static const char *nccl_error(ncclResult_t r) { return g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error"; }
+#define NK(call)                                                                                   \
+  do {                                                                                             \
+    ncclResult_t r_ = (call);                                                                      \
+    if (r_ != ncclSuccess) return fail(FSCL_ERR_CUDA, std::string(#call) + ": " + nccl_error(r_)); \
+  } while (0)
+
+// in place: rank g's bytes_per_rank bytes sit at buf + g * bytes_per_rank
+static int nccl_all_gather(Ctx *c, void *buf, size_t bytes_per_rank) {
+  if (!c->comm || c->world <= 1 || bytes_per_rank == 0) return FSCL_OK;
+  NK(g_nccl.AllGather((const char *)buf + (size_t)c->rank * bytes_per_rank, buf, bytes_per_rank, ncclChar, c->comm, c->stream));
+  return FSCL_OK;
+}
 
 // --------------------------------------------------------------------------- create / destroy
 static void build_alpha_tables(const double *T, AlphaTables &A) {
@@ -604,6 +705,24 @@ extern "C" void fscl_destroy(void *ctx) {
   dev_free(c->d_blkcnt, c->stream); dev_free(c->d_chr_end, c->stream); dev_free(c->d_active[0], c->stream); dev_free(c->d_active[1], c->stream);
   dev_free(c->d_pt_chr, c->stream); dev_free(c->d_pt_sweep, c->stream); dev_free(c->d_pp, c->stream); dev_free(c->d_pn, c->stream); dev_free(c->d_pf, c->stream);
   dev_free(c->d_pt_clr, c->stream); dev_free(c->d_pclr, c->stream); dev_free(c->d_small, c->stream);
+  if (c->prep) cudaStreamSynchronize(c->prep);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  free_tiles(c->ts1, c->stream);
+  dev_free(c->d_pcls1, c->stream); dev_free(c->d_scratch1, c->stream); dev_free(c->d_blkoff1, c->stream);
+  dev_free(c->d_blkcnt1, c->stream); dev_free(c->d_blocks1, c->stream); dev_free(c->d_eng, c->stream);
+  dev_free(c->d_scored, c->stream); dev_free(c->d_totals, c->stream); dev_free(c->d_off, c->stream); dev_free(c->d_pack, c->stream);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (int k = 0; k < 2; k++) {
+    if (c->ev_gen[k]) cudaEventDestroy(c->ev_gen[k]);
+    if (c->ev_prep[k]) cudaEventDestroy(c->ev_prep[k]);
+    if (c->ev_scan[k]) cudaEventDestroy(c->ev_scan[k]);
+  }
+  for (int k = 0; k < 4; k++) {
+    if (c->ev_round[k]) cudaEventDestroy(c->ev_round[k]);
+    if (c->ev_k0[k]) cudaEventDestroy(c->ev_k0[k]);
+    if (c->ev_k1[k]) cudaEventDestroy(c->ev_k1[k]);
+  }
+  if (c->prep) cudaStreamDestroy(c->prep);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -661,8 +780,35 @@ extern "C" int fscl_scan_chromosome(void *ctx, int G, fscl_pt_t *out, int cap, i
   int n = enum_cells(c, G, &c->h_tasks);
   *n_out = n;
   if (n > cap) return fail(FSCL_ERR_ARG, "output capacity too small");
-  int rc = run_tasks(c, false, kFlagNullSum);
-  if (rc) return rc;
+  int rc;
+  if (c->comm && c->world > 1 && n > 0) {
+    // cells shard over the ranks of the communicator (scan_thread's cells are independent,
+    // scan-chromosome.c:162-216); one all-gather of the result records makes every rank complete
+    const size_t chunk = ((size_t)n + c->world - 1) / c->world;
+    const size_t lo = std::min((size_t)n, chunk * c->rank), hi = std::min((size_t)n, lo + chunk);
+    rc = ensure_tasks(c, chunk * c->world); if (rc) return rc;
+    if (hi > lo) {
+      CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data() + lo, (hi - lo) * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaEventRecord(c->ev0, c->stream));
+      launch_scan(c->P, c->d_tasks, c->d_out + lo, c->ts0, (int)(hi - lo), kFlagNullSum | (c->no_prune ? kFlagNoPrune : 0),
+                  c->d_terms, nullptr, c->stream);
+      c->stats.kernel_launches++;
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(c->ev1, c->stream));
+    }
+    rc = nccl_all_gather(c, c->d_out, chunk * sizeof(OutPt)); if (rc) return rc;
+    c->h_out.resize(n);
+    CK(cudaMemcpyAsync(c->h_out.data(), c->d_out, (size_t)n * sizeof(OutPt), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (hi > lo) {
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+      c->stats.score_kernel_ms += ms; c->stats.score_launches++; c->stats.n_tasks += (int64_t)(hi - lo);
+    }
+  } else {
+    rc = run_tasks(c, false, kFlagNullSum);
+    if (rc) return rc;
+  }
   std::vector<fscl_pt_t> pts(n);
   for (int i = 0; i < n; i++) to_pt(c->h_out[i], pts[i]);
   // qsort by (chr, sweep_pos), scan-chromosome.c:264 (stable here)
@@ -740,14 +886,29 @@ extern "C" int fscl_block_permute(void *ctx, const fscl_permute_opts_t *o, int t
   return (int)blocks.size();
 }
 
-// ---- device-resident rounds (counter-based stream) ---------------------------------------------
-static int ensure_pts(Ctx *c, int n_pts, bool want_clr) {
+// ---- device-resident, pipelined rounds (counter-based stream) -------------------------------------
+//
+// A round = R consecutive permutations.  Everything a round needs from the previous one (the active
+// list and its length, the counters) stays on the device; the host only enqueues.  Two streams:
+//
+//   prep   : [wait: scan of round r-2 released this slot set]  gen_blocks(r) -> permute(r) -> bucket(r)
+//   stream : [wait: prep(r)]  taskgen(r) -> scan_cells(r) -> [all-gather over the communicator] ->
+//            replay(r) -> compact(r) -> count to pinned memory
+//
+// The permuted genomes of round r do not depend on the outcome of round r-1 (only the active list
+// does), so prep(r) overlaps scan(r-1): two slot sets alternate.  The host sizes the launches of round
+// r from the active count after round r-2 (read from pinned memory, long complete by then); the
+// kernels take the true count from device memory and surplus CTAs leave at once.  The only host waits
+// are for events that completed a round earlier and for the flags of gen_blocks(r) (about a millisecond,
+// while scan(r-1) keeps the GPU busy), so between two scan kernels the stream holds only
+// replay + compact + taskgen.  Every rank of a sharded run computes the same R from the same stale
+// count, so the round boundaries agree without communication.
+static int ensure_pts(Ctx *c, int n_pts) {
   if (n_pts > c->pts_cap) {
     for (int *&p : {std::ref(c->d_active[0]), std::ref(c->d_active[1]), std::ref(c->d_pt_chr), std::ref(c->d_pt_sweep),
                     std::ref(c->d_pp), std::ref(c->d_pn), std::ref(c->d_pf)}) { if (p) dev_free(p, c->stream); p = nullptr; }
     if (c->d_pt_clr) dev_free(c->d_pt_clr, c->stream);
-    if (c->d_pclr) dev_free(c->d_pclr, c->stream);
-    c->d_pt_clr = nullptr; c->d_pclr = nullptr; c->pclr_alloc = false; c->pts_cap = 0;
+    c->d_pt_clr = nullptr; c->pts_cap = 0;
     const size_t b = sizeof(int) * (size_t)n_pts;
     CK(dev_malloc(&c->d_active[0], b)); CK(dev_malloc(&c->d_active[1], b));
     CK(dev_malloc(&c->d_pt_chr, b)); CK(dev_malloc(&c->d_pt_sweep, b));
@@ -755,9 +916,17 @@ static int ensure_pts(Ctx *c, int n_pts, bool want_clr) {
     CK(dev_malloc(&c->d_pt_clr, sizeof(double) * (size_t)n_pts));
     c->pts_cap = n_pts;
   }
-  if (want_clr && !c->pclr_alloc) {
-    CK(dev_malloc(&c->d_pclr, sizeof(float) * FSCL_NULL_SAVE * (size_t)c->pts_cap));
-    c->pclr_alloc = true;
+  return FSCL_OK;
+}
+
+// stored permuted CLRs on the device: [n_pts][clr_cap] floats
+static int ensure_pclr(Ctx *c, int n_pts, int clr_cap) {
+  const size_t need = (size_t)std::max(n_pts, 1) * (size_t)std::max(clr_cap, 1);
+  if (need > c->pclr_floats) {
+    if (c->d_pclr) dev_free(c->d_pclr, c->stream);
+    c->d_pclr = nullptr; c->pclr_floats = 0;
+    CK(dev_malloc(&c->d_pclr, sizeof(float) * need));
+    c->pclr_floats = need;
   }
   return FSCL_OK;
 }
@@ -775,11 +944,40 @@ static int ensure_small(Ctx *c, int n) {
 // permuted genomes per launch already fill the GPU, cost a quarter of the memory of 256 and waste fewer
 // evaluations on cells that finish inside the round
 constexpr int kMaxRoundPerRank = 64;
+constexpr size_t kSlotMemory = (size_t)12 << 30;      // device memory the two slot sets may take together
+
+static int engine_resources(Ctx *c) {
+  if (c->prep) return FSCL_OK;
+  CK(cudaStreamCreateWithFlags(&c->prep, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaEventCreateWithFlags(&c->ev_gen[k], cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventCreateWithFlags(&c->ev_prep[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_scan[k], cudaEventDisableTiming));
+  }
+  for (int k = 0; k < 4; k++) {
+    CK(cudaEventCreateWithFlags(&c->ev_round[k], cudaEventDisableTiming));
+    CK(cudaEventCreate(&c->ev_k0[k]));
+    CK(cudaEventCreate(&c->ev_k1[k]));
+  }
+  CK(cudaHostAlloc((void **)&c->h_pin, sizeof(int) * (4 + 2 * 3 * kPinSlots), cudaHostAllocDefault));
+  CK(dev_malloc(&c->d_eng, sizeof(int) * (4 + 2 * 3 * kPinSlots)));
+  CK(dev_malloc(&c->d_totals, 2 * sizeof(unsigned long long)));
+  return FSCL_OK;
+}
+
+static int slot_limit(const Ctx *c) {
+  const size_t slot_bytes = (size_t)c->n * 20;        // tiles (key, pos, runs) + classes + scratch
+  return (int)std::max<size_t>(1, std::min<size_t>(kPinSlots, kSlotMemory / 2 / slot_bytes));
+}
 
 static int device_begin(Ctx *c) {
   PermState &S = c->perm;
   const int n = S.n_pts;
-  int rc = ensure_pts(c, std::max(n, 1), S.permute_clr != nullptr); if (rc) return rc;
+  int rc = ensure_pts(c, std::max(n, 1)); if (rc) return rc;
+  rc = engine_resources(c); if (rc) return rc;
+  S.clr_cap = std::min(std::max(S.o.n_permute + 1, 1), FSCL_NULL_SAVE);
+  S.keep_clr = S.permute_clr != nullptr || S.o.save_clr != 0;
+  if (S.keep_clr) { rc = ensure_pclr(c, n, S.clr_cap); if (rc) return rc; }
   std::vector<int> chr(n), sweep(n), pp(n), pn(n), pf(n), act;
   std::vector<double> clr(n);
   for (int i = 0; i < n; i++) {
@@ -800,159 +998,285 @@ static int device_begin(Ctx *c) {
   }
   S.cur = 0;
   S.n_active = (int)act.size();
-  // reserve the permutation slots once: rounds grow as cells are pruned, re-allocating on the way is slow
-  const size_t slot_bytes = (size_t)c->n * 20;        // tiles (key, pos, runs) + classes + scratch
-  int want = (int)std::min<size_t>(kMaxRoundPerRank, std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes));
-  want = std::min(want, S.o.n_permute + 1);
-  if (S.o.round_perms > 0) want = std::min(want, (S.o.round_perms + S.stride - 1) / S.stride);
-  else want = (want + S.stride - 1) / S.stride;
-  return ensure_slots(c, std::max(want, 1));
+  S.round = 0; S.collected = 0;
+  const int counts[3] = {S.n_active, S.n_active, 0};
+  CK(cudaMemcpy(c->d_eng, counts, sizeof counts, cudaMemcpyHostToDevice));
+  CK(cudaMemset(c->d_totals, 0, 2 * sizeof(unsigned long long)));
+  c->set_used[0] = c->set_used[1] = false;
+  // reserve the two permutation slot sets once: rounds grow as cells are pruned, re-allocating on the way is slow
+  int want = std::min(kMaxRoundPerRank, slot_limit(c));
+  want = std::min(want, (S.o.n_permute + S.stride) / S.stride);
+  if (S.o.round_perms > 0) want = std::min(std::min(slot_limit(c), kPinSlots), (S.o.round_perms + S.stride - 1) / S.stride);
+  want = std::max(want, 1);
+  rc = ensure_slots(c, want, 0); if (rc) return rc;
+  if ((long)S.o.n_permute + 1 > (long)want * S.stride) { rc = ensure_slots(c, want, 1); if (rc) return rc; }
+  return FSCL_OK;
 }
 
-// One round with the whole loop body on the GPU: block draws, swap, bucketing, task list, search.
-static int device_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, int *n_active_out) {
+// bookkeeping for the rounds below `upto`, which the host now knows to be complete
+static int engine_collect(Ctx *c, long upto) {
+  PermState &S = c->perm;
+  for (; S.collected < upto; S.collected++) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev_k0[S.collected & 3], c->ev_k1[S.collected & 3]));
+    c->stats.score_kernel_ms += ms;
+  }
+  return FSCL_OK;
+}
+
+static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
   PermState &S = c->perm;
   const fscl_permute_opts_t &o = S.o;
   *R_out = 0;
+  // the active count after round r-2 (the initial one for the first two rounds)
+  const long r = S.round;
+  if (r >= 2) {
+    CK(cudaEventSynchronize(c->ev_round[(r - 2) & 3]));
+    S.n_active = c->h_pin[(r - 2) & 3];
+    int rc = engine_collect(c, r - 1); if (rc) return rc;
+  }
   if (n_active_out) *n_active_out = S.n_active;
   if (S.n_active == 0 || S.t_next > o.n_permute) return FSCL_OK;
   const size_t na = (size_t)S.n_active;
-  // at least 4 permutations per rank and round: the block draws and the swaps of ONE permutation are
-  // serial kernels (a thread / a CTA), so a round of one would leave the GPU idle behind them
+  const int lim = slot_limit(c);
+  // at least 4 permutations per rank and round: the swaps of ONE permutation are a single CTA, so a round
+  // of one would leave most of the GPU idle behind it
   int R = o.round_perms > 0 ? o.round_perms
                             : (int)std::min<size_t>((size_t)kMaxRoundPerRank * S.stride,
                                                     std::max<size_t>(4 * (size_t)S.stride, (16384 + na - 1) / na));
   R = (R + S.stride - 1) / S.stride * S.stride;
-  const size_t slot_bytes = (size_t)c->n * 20;
-  const int mem_cap = (int)std::max<size_t>(1, ((size_t)8 << 30) / slot_bytes);
-  R = std::min(R, mem_cap * S.stride);
+  R = std::min(R, lim * S.stride);
   R = std::min(R, o.n_permute - S.t_next + 1);
-  if (d_matrix && (int64_t)na > cap) return fail(FSCL_ERR_ARG, "clr matrix too small for one permutation");
-  if (d_matrix && (int64_t)R * (int64_t)na > cap) R = (int)std::max<int64_t>(1, cap / (int64_t)na);
-  std::vector<int> tl, rows;
-  for (int r = 0; r < R; r++)
-    if (((S.t_next + r) % S.stride) == o.first_perm) { tl.push_back(S.t_next + r); rows.push_back(r); }
-  const int ns = (int)tl.size();
-  double *dm = d_matrix;
-  if (!dm) {
-    const size_t need = (size_t)R * na;
+  std::vector<int> tl;
+  for (int q = 0; q < R; q++)
+    if (((S.t_next + q) % S.stride) == o.first_perm) tl.push_back(S.t_next + q);
+  const int ns = (int)tl.size(), ns_max = (R + S.stride - 1) / S.stride;
+  const int set = (int)(r & 1);
+  int rc = ensure_slots(c, ns_max, set); if (rc) return rc;
+  SlotRef Q = slot_set(c, set);
+  const size_t chunk = (size_t)ns_max * na;
+  {
+    const size_t need = chunk * (size_t)c->world;
     if (need > c->matrix_cap) {
+      CK(cudaStreamSynchronize(c->stream));
       if (c->d_matrix) dev_free(c->d_matrix, c->stream);
       c->d_matrix = nullptr; c->matrix_cap = 0;
       CK(dev_malloc(&c->d_matrix, need * sizeof(double)));
       c->matrix_cap = need;
     }
-    dm = c->d_matrix;
-  }
-  S.d_matrix = dm;
-  int rc = ensure_small(c, std::max(R, 1)); if (rc) return rc;
-  const int sc = c->small_cap;
-  int *d_tl = c->d_small, *d_rows = c->d_small + sc, *d_flags = c->d_small + 2 * sc, *d_d7 = c->d_small + 3 * sc;
-  if (ns < R) CK(cudaMemsetAsync(dm, 0, (size_t)R * na * sizeof(double), c->stream));
-  if (ns > 0) {
-    rc = ensure_slots(c, ns); if (rc) return rc;
-    const int stride = c->n / 4 + 1024;                       // block-list capacity per permutation
-    if ((size_t)ns * stride > c->blocks_cap) {
-      if (c->d_blocks) dev_free(c->d_blocks, c->stream);
-      c->d_blocks = nullptr; c->blocks_cap = 0;
-      CK(dev_malloc(&c->d_blocks, (size_t)ns * stride * sizeof(int4)));
-      c->blocks_cap = (size_t)ns * stride;
+    if (R > c->scored_cap) {
+      CK(cudaStreamSynchronize(c->stream));
+      if (c->d_scored) dev_free(c->d_scored, c->stream);
+      c->d_scored = nullptr; c->scored_cap = 0;
+      const int cap = std::max(R, 256);
+      CK(dev_malloc(&c->d_scored, sizeof(int) * (size_t)cap));
+      CK(cudaMemset(c->d_scored, 0, sizeof(int) * (size_t)cap));
+      c->scored_cap = cap;
     }
-    CK(cudaMemcpyAsync(d_tl, tl.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(d_rows, rows.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
+    if (chunk > c->tasks_cap) {
+      CK(cudaStreamSynchronize(c->stream));
+      rc = ensure_tasks(c, chunk); if (rc) return rc;
+    }
+  }
+  int *d_cnt = c->d_eng + S.cur;                            // active count going into this round
+  int *d_ntasks = c->d_eng + 2;
+  int *d_tl = c->d_eng + 4 + set * 3 * kPinSlots, *d_flags = d_tl + kPinSlots, *d_d7 = d_flags + kPinSlots;
+  int *h_flags = c->h_pin + 4 + set * 3 * kPinSlots, *h_d7 = h_flags + kPinSlots, *h_cnt = h_d7 + kPinSlots;
+  if (ns > 0) {
+    // ---- prep stream: the permuted genomes of this round ----
+    if (c->set_used[set]) CK(cudaStreamWaitEvent(c->prep, c->ev_scan[set], 0));      // the scan of round r-2 read this set
+    const int stride = c->n / 4 + 1024;                       // block-list capacity per permutation
+    if ((size_t)ns_max * stride > Q.blocks_cap) {
+      CK(cudaStreamSynchronize(c->prep));
+      if (Q.blocks) dev_free(Q.blocks, c->prep);
+      Q.blocks = nullptr; Q.blocks_cap = 0;
+      CK(dev_malloc(&Q.blocks, (size_t)ns_max * stride * sizeof(int4)));
+      Q.blocks_cap = (size_t)ns_max * stride;
+    }
     std::vector<int> starts(ns);
     for (int q = 0; q < ns; q++) starts[q] = q * stride;
-    CK(cudaMemcpyAsync(c->d_blkoff, starts.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaEventRecord(c->ev0, c->stream));
-    launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o.seed, d_tl, o.permute_nbp, o.scan_width_mb * 1e6, c->d_blocks,
-                      stride, c->d_blkcnt, d_flags, d_d7, ns, c->stream);
+    CK(cudaMemcpyAsync(d_tl, tl.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->prep));
+    CK(cudaMemcpyAsync(Q.blkoff, starts.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->prep));
+    launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o.seed, d_tl, o.permute_nbp, o.scan_width_mb * 1e6, Q.blocks,
+                      stride, Q.blkcnt, d_flags, d_d7, ns, c->prep, d_cnt);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    std::vector<int> flags(ns), d7(ns), cnt(ns);
-    CK(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(d7.data(), d_d7, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(cnt.data(), c->d_blkcnt, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(h_flags, d_flags, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->prep));
+    CK(cudaMemcpyAsync(h_d7, d_d7, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->prep));
+    CK(cudaMemcpyAsync(h_cnt, Q.blkcnt, sizeof(int) * ns, cudaMemcpyDeviceToHost, c->prep));
+    CK(cudaEventRecord(c->ev_gen[set], c->prep));
+    CK(cudaEventSynchronize(c->ev_gen[set]));                 // the draws only; the previous round's scan is still running
     bool redo = false;
     for (int q = 0; q < ns; q++) {
-      if (flags[q] & 6) redo = true;                          // ambiguous truncation or overflow: host draws
-      c->stats.d7_hits += d7[q];
-      c->stats.n_blocks += cnt[q];
+      if (h_flags[q] & 6) redo = true;                        // ambiguous truncation or overflow: host draws
+      c->stats.d7_hits += h_d7[q];
+      c->stats.n_blocks += h_cnt[q];
     }
     if (redo) {
       BlockGen gen{c->n, c->h_pos.data(), c->chr_end_index.data(), o.permute_nbp, o.scan_width_mb * 1e6};
-      std::vector<int4> blocks; std::vector<int> off(1, 0);
+      std::vector<int4> blocks; std::vector<int> off(1, 0), cnt(ns);
       int dd = 0;
       for (int q = 0; q < ns; q++) { S.src.set_perm((uint32_t)tl[q]); gen.generate(S.src, blocks, &dd); off.push_back((int)blocks.size()); }
-      rc = upload_blocks(c, blocks, off); if (rc) return rc;
+      if (blocks.size() > Q.blocks_cap) {
+        CK(cudaStreamSynchronize(c->prep));
+        if (Q.blocks) dev_free(Q.blocks, c->prep);
+        Q.blocks = nullptr; Q.blocks_cap = 0;
+        CK(dev_malloc(&Q.blocks, (blocks.size() + 1024) * sizeof(int4)));
+        Q.blocks_cap = blocks.size() + 1024;
+      }
+      for (int q = 0; q < ns; q++) cnt[q] = off[q + 1] - off[q];
+      CK(cudaMemcpyAsync(Q.blocks, blocks.data(), blocks.size() * sizeof(int4), cudaMemcpyHostToDevice, c->prep));
+      CK(cudaMemcpyAsync(Q.blkoff, off.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->prep));
+      CK(cudaMemcpyAsync(Q.blkcnt, cnt.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->prep));
+      CK(cudaStreamSynchronize(c->prep));                     // the vectors are locals
     }
-    launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, ns, c->stream);
+    launch_permute(c->n, c->d_cls0, Q.pcls, Q.scratch, Q.blocks, Q.blkoff, Q.blkcnt, ns, c->prep, d_cnt);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->ts, ns,
-                  c->stream);
+    launch_bucket(c->n, c->n_pad, Q.pcls, (size_t)c->n, c->d_pos, c->d_null, Q.ts, ns, c->prep, d_cnt);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(c->ev1, c->stream));
-    rc = ensure_tasks(c, (size_t)ns * na); if (rc) return rc;
-    launch_taskgen((int)na, ns, c->d_active[S.cur], d_rows, c->d_pt_chr, c->d_pt_sweep, o.large_grid_sp, c->d_tasks,
-                   c->stream);
+    CK(cudaEventRecord(c->ev_prep[set], c->prep));
+    c->stats.permute_launches++;
+    // ---- scan stream ----
+    CK(cudaStreamWaitEvent(c->stream, c->ev_prep[set], 0));
+    launch_taskgen((int)na, ns, c->d_active[S.cur], d_cnt, c->d_pt_chr, c->d_pt_sweep, o.large_grid_sp, c->d_tasks, d_ntasks,
+                   c->d_totals, c->stream);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    cudaEvent_t e2 = c->ev2, e3 = c->ev3;
-    CK(cudaEventRecord(e2, c->stream));
-    launch_scan(c->P, c->d_tasks, c->d_out, c->ts, (int)((size_t)ns * na), c->no_prune ? kFlagNoPrune : 0, c->d_terms, dm,
-                c->stream);
+    CK(cudaEventRecord(c->ev_k0[r & 3], c->stream));
+    launch_scan(c->P, c->d_tasks, nullptr, Q.ts, (int)((size_t)ns * na), c->no_prune ? kFlagNoPrune : 0, c->d_terms,
+                c->d_matrix + (size_t)c->rank * chunk, c->stream, d_ntasks);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    CK(cudaEventRecord(e3, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    c->stats.permute_kernel_ms += ms; c->stats.permute_launches++;
-    CK(cudaEventElapsedTime(&ms, e2, e3));
-    c->stats.score_kernel_ms += ms; c->stats.score_launches++;
-    c->stats.n_tasks += (int64_t)ns * (int64_t)na;
-    c->stats.n_grid_evals += (int64_t)ns * (int64_t)na;
+    CK(cudaEventRecord(c->ev_k1[r & 3], c->stream));
+    CK(cudaEventRecord(c->ev_scan[set], c->stream));
+    c->set_used[set] = true;
+    c->stats.score_launches++;
   } else {
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->ev_k0[r & 3], c->stream));
+    CK(cudaEventRecord(c->ev_k1[r & 3], c->stream));
   }
-  S.R = R;
+  S.R = R; S.na_round = (int)na; S.ns_round = ns; S.chunk = chunk;
   *R_out = R;
   return FSCL_OK;
 }
 
-static int device_round_commit(Ctx *c, const double *d_matrix) {
+static int device_round_commit(Ctx *c) {
   PermState &S = c->perm;
   const fscl_permute_opts_t &o = S.o;
-  const double *dm = d_matrix ? d_matrix : S.d_matrix;
-  const int sc = c->small_cap;
-  int *d_scored = c->d_small + 4 * sc, *d_count = c->d_small + 5 * sc;
-  CK(cudaMemsetAsync(d_scored, 0, sizeof(int) * S.R, c->stream));
-  launch_replay(S.n_active, S.R, S.t_next, c->d_active[S.cur], dm, c->d_pt_clr, c->d_pp, c->d_pn, c->d_pf,
-                S.permute_clr ? c->d_pclr : nullptr, o.seed, o.prune, d_scored, c->stream);
+  const long r = S.round;
+  if (c->world > 1) {
+    int rc = nccl_all_gather(c, c->d_matrix, S.chunk * sizeof(double)); if (rc) return rc;
+  }
+  int *d_cnt = c->d_eng + S.cur, *d_cnt_next = c->d_eng + (S.cur ^ 1);
+  launch_replay(S.na_round, d_cnt, S.R, S.t_next, S.stride, S.chunk, c->d_active[S.cur], c->d_matrix, c->d_pt_clr, c->d_pp,
+                c->d_pn, c->d_pf, S.keep_clr ? c->d_pclr : nullptr, S.clr_cap, o.seed, o.prune, c->d_scored, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
-  launch_compact(S.n_active, c->d_active[S.cur], c->d_pf, c->d_active[S.cur ^ 1], d_count, c->stream);
+  launch_compact(S.na_round, d_cnt, c->d_active[S.cur], c->d_pf, c->d_active[S.cur ^ 1], d_cnt_next, c->d_scored, S.R,
+                 c->d_totals + 1, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
-  std::vector<int> scored(S.R);
-  int count = 0;
-  CK(cudaMemcpyAsync(scored.data(), d_scored, sizeof(int) * S.R, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  for (int r = 0; r < S.R; r++) c->stats.n_scored += scored[r];
+  CK(cudaMemcpyAsync(c->h_pin + (r & 3), d_cnt_next, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaEventRecord(c->ev_round[r & 3], c->stream));
   S.cur ^= 1;
-  S.n_active = count;
   c->stats.n_rounds++;
   S.t_next += S.R;
   S.R = 0;
+  S.round = r + 1;
+  return FSCL_OK;
+}
+
+// wait for everything enqueued, bring the host-side view (active count, timings, totals) up to date
+static int device_drain(Ctx *c) {
+  PermState &S = c->perm;
+  CK(cudaStreamSynchronize(c->prep));
+  CK(cudaStreamSynchronize(c->stream));
+  { int rc = engine_collect(c, S.round); if (rc) return rc; }
+  if (S.round > 0) S.n_active = c->h_pin[(S.round - 1) & 3];
+  S.round = 0; S.collected = 0;                    // the ring starts over: the next round waits for nothing
+  const int counts[2] = {S.n_active, S.n_active};
+  CK(cudaMemcpy(c->d_eng, counts, sizeof counts, cudaMemcpyHostToDevice));
+  unsigned long long tot[2] = {0, 0};
+  CK(cudaMemcpy(tot, c->d_totals, sizeof tot, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(c->d_totals, 0, sizeof tot));
+  c->stats.n_tasks += (int64_t)tot[0];
+  c->stats.n_grid_evals += (int64_t)tot[0];
+  c->stats.n_scored += (int64_t)tot[1];
+  return FSCL_OK;
+}
+
+// stored CLRs: device table <-> host, one kernel + one copy.  pn = permute_n per cell.
+// dense != NULL: rows of FSCL_NULL_SAVE floats; else packed (cell i at off[i]).
+static int clr_offsets(const std::vector<int> &pn, int clr_cap, std::vector<long long> &off) {
+  off.resize(pn.size() + 1);
+  off[0] = 0;
+  for (size_t i = 0; i < pn.size(); i++) off[i + 1] = off[i] + std::min(std::max(pn[i], 0), clr_cap);
+  return FSCL_OK;
+}
+
+static int ensure_pack(Ctx *c, int n_pts, size_t total) {
+  if (n_pts + 1 > c->off_cap) {
+    if (c->d_off) dev_free(c->d_off, c->stream);
+    c->d_off = nullptr; c->off_cap = 0;
+    CK(dev_malloc(&c->d_off, sizeof(long long) * (size_t)(n_pts + 1)));
+    c->off_cap = n_pts + 1;
+  }
+  if (total > c->pack_cap) {
+    if (c->d_pack) dev_free(c->d_pack, c->stream);
+    c->d_pack = nullptr; c->pack_cap = 0;
+    CK(dev_malloc(&c->d_pack, sizeof(float) * std::max<size_t>(total, 1)));
+    c->pack_cap = std::max<size_t>(total, 1);
+  }
+  return FSCL_OK;
+}
+
+static int clr_to_host(Ctx *c, const std::vector<int> &pn, float *dense, float *packed, const std::vector<long long> &off) {
+  PermState &S = c->perm;
+  const int n = (int)pn.size();
+  const size_t total = (size_t)off[n];
+  if (n == 0 || total == 0) return FSCL_OK;
+  int rc = ensure_pack(c, n, total); if (rc) return rc;
+  CK(cudaMemcpyAsync(c->d_off, off.data(), sizeof(long long) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+  launch_pack_clr(n, c->d_pn, c->d_off, S.clr_cap, c->d_pclr, c->d_pack, 0, c->stream);
+  c->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  std::vector<float> tmp;
+  float *dst = packed;
+  if (!dst) { tmp.resize(total); dst = tmp.data(); }
+  CK(cudaMemcpyAsync(dst, c->d_pack, sizeof(float) * total, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  if (dense)
+    for (int i = 0; i < n; i++)
+      if (off[i + 1] > off[i]) memcpy(dense + (size_t)i * FSCL_NULL_SAVE, dst + off[i], sizeof(float) * (size_t)(off[i + 1] - off[i]));
+  return FSCL_OK;
+}
+
+static int clr_to_device(Ctx *c, const std::vector<int> &pn, const float *dense) {
+  PermState &S = c->perm;
+  const int n = (int)pn.size();
+  std::vector<long long> off;
+  clr_offsets(pn, S.clr_cap, off);
+  const size_t total = (size_t)off[n];
+  if (n == 0 || total == 0) return FSCL_OK;
+  int rc = ensure_pack(c, n, total); if (rc) return rc;
+  std::vector<float> tmp(total);
+  for (int i = 0; i < n; i++)
+    if (off[i + 1] > off[i]) memcpy(tmp.data() + off[i], dense + (size_t)i * FSCL_NULL_SAVE, sizeof(float) * (size_t)(off[i + 1] - off[i]));
+  CK(cudaMemcpyAsync(c->d_off, off.data(), sizeof(long long) * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_pack, tmp.data(), sizeof(float) * total, cudaMemcpyHostToDevice, c->stream));
+  launch_pack_clr(n, c->d_pn, c->d_off, S.clr_cap, c->d_pclr, c->d_pack, 1, c->stream);
+  c->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
   return FSCL_OK;
 }
 
 static int device_end(Ctx *c) {
   PermState &S = c->perm;
   const int n = S.n_pts;
+  int rc = device_drain(c); if (rc) return rc;
   if (n == 0) return FSCL_OK;
   std::vector<int> pp(n), pn(n), pf(n);
   const size_t b = sizeof(int) * (size_t)n;
@@ -961,13 +1285,10 @@ static int device_end(Ctx *c) {
   CK(cudaMemcpy(pf.data(), c->d_pf, b, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) { S.pts[i].permute_p = pp[i]; S.pts[i].permute_n = pn[i]; S.pts[i].permute_finished = pf[i]; }
   if (S.permute_clr) {
-    // only the entries written are meaningful (first permute_n, at most FSCL_NULL_SAVE)
-    std::vector<float> row(FSCL_NULL_SAVE);
-    for (int i = 0; i < n; i++) {
-      const int m = std::min(pn[i], FSCL_NULL_SAVE);
-      if (m > 0) CK(cudaMemcpy(S.permute_clr + (size_t)i * FSCL_NULL_SAVE, c->d_pclr + (size_t)i * FSCL_NULL_SAVE,
-                               sizeof(float) * m, cudaMemcpyDeviceToHost));
-    }
+    // only the entries written are meaningful (first permute_n, at most clr_cap)
+    std::vector<long long> off;
+    clr_offsets(pn, S.clr_cap, off);
+    rc = clr_to_host(c, pn, S.permute_clr, nullptr, off); if (rc) return rc;
   }
   return FSCL_OK;
 }
@@ -996,9 +1317,18 @@ static int perm_begin(Ctx *c, fscl_pt_t *pts, int n_pts, const fscl_permute_opts
   for (int i = 0; i < n_pts; i++) S.active[i] = i;
   S.t_next = 0;
   S.open = true;
+  S.rounds_at_begin = c->stats.n_rounds;
   // counter-based stream: the loop body lives on the GPU (FSCL_B200_HOST_ROUNDS=1 keeps the host path)
   const char *hr = getenv("FSCL_B200_HOST_ROUNDS");
   S.on_device = !S.src.sequential() && !(hr && atoi(hr) != 0);
+  if (c->comm) {
+    // sharded over the communicator: rank g scores the permutations t with t % world == g
+    if (S.src.sequential()) return fail(FSCL_ERR_ARG, "sequential RNG streams cannot be sharded");
+    S.stride = c->world; S.o.first_perm = c->rank; S.o.perm_stride = c->world;
+    if (!S.on_device) return fail(FSCL_ERR_ARG, "FSCL_B200_HOST_ROUNDS cannot be combined with a communicator");
+  } else if (S.stride > 1) {
+    S.on_device = false;      // the caller sums an external matrix over its own ranks: synchronous host rounds
+  }
   if (S.on_device) {
     CK(cudaSetDevice(c->device));
     return device_begin(c);
@@ -1011,7 +1341,13 @@ static int perm_round_score(Ctx *c, double *d_matrix, int64_t cap, int *R_out, i
   PermState &S = c->perm;
   if (!S.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
   CK(cudaSetDevice(c->device));
-  if (S.on_device) return device_round_score(c, d_matrix, cap, R_out, n_active_out);
+  if (S.on_device && d_matrix) {
+    // an external matrix means the caller runs the collective itself: that needs the synchronous host rounds
+    if (S.round != 0 || c->stats.n_rounds != S.rounds_at_begin || c->comm)
+      return fail(FSCL_ERR_ARG, "an external CLR matrix must be used from the first round on (and without a communicator)");
+    S.on_device = false;
+  }
+  if (S.on_device) return device_round_score(c, R_out, n_active_out);
   const fscl_permute_opts_t &o = S.o;
   const int G = o.large_grid_sp;
   fscl_pt_t *pts = S.pts;
@@ -1096,7 +1432,7 @@ static int perm_round_commit(Ctx *c, const double *d_matrix) {
   PermState &S = c->perm;
   if (!S.open || S.R <= 0) return fail(FSCL_ERR_ARG, "no scored round to commit");
   CK(cudaSetDevice(c->device));
-  if (S.on_device) return device_round_commit(c, d_matrix);
+  if (S.on_device) return device_round_commit(c);
   const fscl_permute_opts_t &o = S.o;
   const size_t na = S.active.size();
   const double *dm = d_matrix ? d_matrix : S.d_matrix;
@@ -1143,7 +1479,6 @@ extern "C" int fscl_perm_snapshot(void *ctx, int32_t *t_next_out) {
   if (!c || !c->perm.open) return fail(FSCL_ERR_ARG, "no permutation test in progress");
   if (c->perm.on_device) {
     CK(cudaSetDevice(c->device));
-    CK(cudaStreamSynchronize(c->stream));
     int rc = device_end(c);
     if (rc) return rc;
   }
@@ -1163,11 +1498,9 @@ extern "C" int fscl_perm_seek(void *ctx, int32_t t_next) {
   S.t_next = t_next;
   if (S.on_device && S.permute_clr) {
     CK(cudaSetDevice(c->device));
-    for (int i = 0; i < S.n_pts; i++) {
-      const int m = std::min(S.pts[i].permute_n, FSCL_NULL_SAVE);
-      if (m > 0) CK(cudaMemcpy(c->d_pclr + (size_t)i * FSCL_NULL_SAVE, S.permute_clr + (size_t)i * FSCL_NULL_SAVE,
-                               sizeof(float) * m, cudaMemcpyHostToDevice));
-    }
+    std::vector<int> pn(S.n_pts);
+    for (int i = 0; i < S.n_pts; i++) pn[i] = S.pts[i].permute_n;
+    return clr_to_device(c, pn, S.permute_clr);
   }
   return FSCL_OK;
 }
@@ -1175,8 +1508,8 @@ extern "C" int fscl_perm_seek(void *ctx, int32_t t_next) {
 extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fscl_permute_opts_t *o,
                                  float *permute_clr, fscl_stats_t *stats_out) {
   Ctx *c = (Ctx *)ctx;
-  if (o && o->perm_stride > 1)
-    return fail(FSCL_ERR_ARG, "sharded runs must use the round API and sum the matrix across ranks");
+  if (o && o->perm_stride > 1 && !(c && c->comm))
+    return fail(FSCL_ERR_ARG, "sharded runs need a communicator (fscl_comm_init_*) or the round API with an external matrix");
   int rc = perm_begin(c, pts, n_pts, o, permute_clr);
   if (rc) return rc;
   for (;;) {
@@ -1188,6 +1521,120 @@ extern "C" int fscl_scan_permute(void *ctx, fscl_pt_t *pts, int n_pts, const fsc
     if (rc) return rc;
   }
   return fscl_perm_end(c, stats_out);
+}
+
+// --------------------------------------------------------------------------- multi-GPU (NCCL)
+// The reference's fscl-master.c:1-18 is an unfinished master / slave split; here the permutation
+// replicates shard over the GPUs of one box: rank g scores the permutations
+// t = g (mod world) of every round into its own rows of the round's CLR matrix, ONE ncclAllGather per
+// round (on the library's stream, NVLink / NVSwitch) makes the matrix complete on every rank, and
+// every rank replays the same sequential counting / pruning rule -- counts are identical on all ranks
+// and independent of the number of GPUs.  libnccl.so.2 is resolved at run time (dlopen), so the
+// library loads and runs on one GPU without NCCL; in a process that already holds NCCL (torch) the
+// loader hands back that copy.
+extern "C" int fscl_comm_unique_id(char *id128) {
+  if (!id128) return fail(FSCL_ERR_ARG, "bad argument");
+  int rc = nccl_load(); if (rc) return rc;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  NK(g_nccl.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return FSCL_OK;
+}
+
+extern "C" int fscl_comm_init_rank(void *ctx, int world, int rank, const char *id128) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(FSCL_ERR_ARG, "bad argument");
+  if (c->comm) return fail(FSCL_ERR_ARG, "context already has a communicator");
+  int rc = nccl_load(); if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  NK(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->world = world; c->rank = rank;
+  return FSCL_OK;
+}
+
+// one process, n contexts on n different devices
+extern "C" int fscl_comm_init_all(void **ctxs, int n) {
+  if (!ctxs || n < 1 || n > kMaxDevices) return fail(FSCL_ERR_ARG, "bad argument");
+  int rc = nccl_load(); if (rc) return rc;
+  std::vector<int> devs(n);
+  std::vector<ncclComm_t> comms(n);
+  for (int i = 0; i < n; i++) {
+    Ctx *c = (Ctx *)ctxs[i];
+    if (!c || c->comm) return fail(FSCL_ERR_ARG, "bad context in the list");
+    devs[i] = c->device;
+    for (int j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(FSCL_ERR_ARG, "two contexts on one device");
+  }
+  NK(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; i++) { Ctx *c = (Ctx *)ctxs[i]; c->comm = comms[i]; c->world = n; c->rank = i; }
+  return FSCL_OK;
+}
+
+extern "C" int fscl_comm_destroy(void *ctx) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  if (c->comm) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    g_nccl.CommDestroy(c->comm);
+  }
+  c->comm = nullptr; c->world = 1; c->rank = 0;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_comm_info(void *ctx, int *world, int *rank) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "bad argument");
+  if (world) *world = c->world;
+  if (rank) *rank = c->rank;
+  return FSCL_OK;
+}
+
+// ---- stored permuted CLRs and the projection, device-resident ----------------------------------
+// After fscl_perm_end / fscl_perm_snapshot of a test begun with permute_clr != NULL or opts.save_clr:
+// offsets[n_pts + 1] (cell i holds offsets[i+1] - offsets[i] = min(permute_n, FSCL_NULL_SAVE, n_permute + 1)
+// values); packed == NULL only fills the offsets (size the buffer with offsets[n_pts] floats first).
+extern "C" int fscl_perm_fetch_clr(void *ctx, int64_t *offsets, float *packed, int64_t cap) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !offsets) return fail(FSCL_ERR_ARG, "bad argument");
+  PermState &S = c->perm;
+  if (!S.on_device || !S.keep_clr || !c->d_pclr) return fail(FSCL_ERR_ARG, "no permuted CLRs were kept on the device for this test");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  const int n = S.n_pts;
+  std::vector<int> pn(n);
+  if (n > 0) CK(cudaMemcpy(pn.data(), c->d_pn, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost));
+  std::vector<long long> off;
+  clr_offsets(pn, S.clr_cap, off);
+  for (int i = 0; i <= n; i++) offsets[i] = off[i];
+  if (!packed) return FSCL_OK;
+  if (cap < off[n]) return fail(FSCL_ERR_ARG, "packed buffer too small");
+  return clr_to_host(c, pn, nullptr, packed, off);
+}
+
+// p-value projection on the device from the CLRs kept there (definition: DESIGN.md 3.6; the reference
+// describes it at README.md:11 and never implemented it)
+extern "C" int fscl_perm_project(void *ctx, double df, double *lambda_out, double *p_out) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !p_out || !(df > 0)) return fail(FSCL_ERR_ARG, "bad argument");
+  PermState &S = c->perm;
+  if (!S.on_device || !S.keep_clr || !c->d_pclr) return fail(FSCL_ERR_ARG, "no permuted CLRs were kept on the device for this test");
+  CK(cudaSetDevice(c->device));
+  const int n = S.n_pts;
+  if (n == 0) return FSCL_OK;
+  double *d_out = nullptr;
+  CK(dev_malloc(&d_out, sizeof(double) * 2 * (size_t)n));
+  launch_project(n, c->d_pn, c->d_pt_clr, c->d_pclr, S.clr_cap, df, d_out, d_out + n, c->stream);
+  c->stats.kernel_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess && lambda_out) e = cudaMemcpyAsync(lambda_out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p_out, d_out + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  dev_free(d_out, c->stream);
+  if (e != cudaSuccess) return fail(FSCL_ERR_CUDA, std::string("projection: ") + cudaGetErrorString(e));
+  return FSCL_OK;
 }
 
 // Block list of permutation t drawn ON THE DEVICE (gen_blocks_kernel); test hook.
@@ -1207,16 +1654,22 @@ extern "C" int fscl_device_gen_blocks(void *ctx, const fscl_permute_opts_t *o, i
   }
   const int sc = c->small_cap;
   int *d_tl = c->d_small, *d_flags = c->d_small + 2 * sc, *d_d7 = c->d_small + 3 * sc;
-  cudaMemcpy(d_tl, &t, sizeof(int), cudaMemcpyHostToDevice);
+  auto bad = [&](cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return false;
+    fail(FSCL_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return true;
+  };
+  if (bad(cudaMemcpy(d_tl, &t, sizeof(int), cudaMemcpyHostToDevice), "gen_blocks: upload")) return -1;
   launch_gen_blocks(c->n, c->d_pos, c->d_chr_end, o->seed, d_tl, o->permute_nbp, o->scan_width_mb * 1e6, c->d_blocks,
                     stride, c->d_blkcnt, d_flags, d_d7, 1, c->stream);
   c->stats.kernel_launches++;
   int cnt = 0, flags = 0;
-  if (cudaStreamSynchronize(c->stream) != cudaSuccess) { fail(FSCL_ERR_CUDA, "gen_blocks_kernel"); return -1; }
-  cudaMemcpy(&cnt, c->d_blkcnt, sizeof(int), cudaMemcpyDeviceToHost);
-  cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost);
-  std::vector<int4> b(std::min(cnt, stride));
-  if (!b.empty()) cudaMemcpy(b.data(), c->d_blocks, sizeof(int4) * b.size(), cudaMemcpyDeviceToHost);
+  if (bad(cudaGetLastError(), "gen_blocks_kernel launch")) return -1;
+  if (bad(cudaStreamSynchronize(c->stream), "gen_blocks_kernel")) return -1;
+  if (bad(cudaMemcpy(&cnt, c->d_blkcnt, sizeof(int), cudaMemcpyDeviceToHost), "gen_blocks: count")) return -1;
+  if (bad(cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost), "gen_blocks: flags")) return -1;
+  std::vector<int4> b(std::max(0, std::min(cnt, stride)));
+  if (!b.empty() && bad(cudaMemcpy(b.data(), c->d_blocks, sizeof(int4) * b.size(), cudaMemcpyDeviceToHost), "gen_blocks: list")) return -1;
   for (size_t q = 0; q < b.size() && blocks_out && (int)q < max_blocks; q++) {
     blocks_out[3 * q] = b[q].x; blocks_out[3 * q + 1] = b[q].y; blocks_out[3 * q + 2] = b[q].z;
   }
@@ -1328,61 +1781,8 @@ extern "C" int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint
 // from the actual data CLR to infinity".  The reference never implemented it, so
 // this is a DEFINITION, not a port: df is fixed by the caller (default 2: sweep position and strength),
 // lambda = max(mean of the stored permuted CLRs - df, 0) (method of moments), p = P[ncx2(df, lambda) >= CLR].
-namespace {
-// regularised upper incomplete gamma Q(a, x), a > 0, x >= 0 (series below a+1, Lentz continued fraction above)
-double gamma_q(double a, double x) {
-  if (x <= 0.0) return 1.0;
-  const double lg = std::lgamma(a);
-  if (x < a + 1.0) {
-    double ap = a, sum = 1.0 / a, del = sum;
-    for (int n = 0; n < 10000; n++) {
-      ap += 1.0; del *= x / ap; sum += del;
-      if (std::fabs(del) < std::fabs(sum) * 1e-17) break;
-    }
-    return 1.0 - sum * std::exp(-x + a * std::log(x) - lg);
-  }
-  const double tiny = 1e-300;
-  double b = x + 1.0 - a, c = 1.0 / tiny, d = 1.0 / b, h = d;
-  for (int i = 1; i < 10000; i++) {
-    const double an = -i * (i - a);
-    b += 2.0;
-    d = an * d + b; if (std::fabs(d) < tiny) d = tiny;
-    c = b + an / c; if (std::fabs(c) < tiny) c = tiny;
-    d = 1.0 / d;
-    const double del = d * c;
-    h *= del;
-    if (std::fabs(del - 1.0) < 1e-16) break;
-  }
-  return std::exp(-x + a * std::log(x) - lg) * h;
-}
-
-// survival function of the non-central chi-square: Poisson(lambda/2) mixture of central ones,
-// summed outwards from the Poisson mode so that tiny tails keep their relative accuracy
-double ncx2_sf(double x, double df, double lambda) {
-  if (x <= 0.0) return 1.0;
-  if (lambda <= 0.0) return gamma_q(0.5 * df, 0.5 * x);
-  const double mu = 0.5 * lambda;
-  const int mode = (int)mu;
-  auto logpois = [&](int i) { return -mu + i * std::log(mu) - std::lgamma(i + 1.0); };
-  double total = 0.0;
-  double w = std::exp(logpois(mode));
-  double wi = w;
-  for (int i = mode; i < mode + 100000; i++) {          // upwards
-    const double term = wi * gamma_q(0.5 * df + i, 0.5 * x);
-    total += term;
-    if (i > mode && wi < 1e-18 * w && term < 1e-17 * total) break;
-    wi *= mu / (i + 1.0);
-  }
-  wi = w;
-  for (int i = mode - 1; i >= 0; i--) {                  // downwards
-    wi *= (i + 1.0) / mu;
-    const double term = wi * gamma_q(0.5 * df + i, 0.5 * x);
-    total += term;
-    if (wi < 1e-18 * w && term < 1e-17 * total) break;
-  }
-  return total > 1.0 ? 1.0 : total;
-}
-}  // namespace
+#include "fscl_ncx2.cuh"
+using fscl::ncx2_sf;
 
 extern "C" int fscl_ncx2_sf(int n, const double *x, double df, const double *lambda, double *out) {
   if (n < 0 || !x || !lambda || !out || !(df > 0)) return fail(FSCL_ERR_ARG, "bad argument");

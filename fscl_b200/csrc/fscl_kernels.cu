@@ -1,5 +1,6 @@
 // fscl_kernels.cu -- sm_100a kernels (see fscl_kernels.cuh for the reference map).
 #include "fscl_kernels.cuh"
+#include "fscl_ncx2.cuh"
 
 namespace fscl {
 
@@ -553,7 +554,11 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
                   const int *__restrict__ tkey_all, const int *__restrict__ tpos_all,
                   const double *__restrict__ tnull_all, const int *__restrict__ trun_all,
                   const int *__restrict__ tnrun_all, const int *__restrict__ icls_all, size_t icls_stride,
-                  int flags, unsigned long long *term_counter, double *__restrict__ clr_matrix) {
+                  int flags, unsigned long long *term_counter, double *__restrict__ clr_matrix,
+                  const int *__restrict__ n_tasks_dev) {
+  // pipelined permutation rounds size the grid from a stale (larger) active count; the true task
+  // count of the round lives on the device (taskgen_kernel)
+  if (n_tasks_dev && (int)blockIdx.x >= *n_tasks_dev) return;
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
@@ -644,7 +649,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     o.chr = t.chr; o.nearest = A.nearest; o.sweep_pos = A.sweep_pos;
     o.n_snps = A.wend - A.wstart + 1; o.wstart = A.wstart; o.wend = A.wend;
     o.lalpha = A.lalpha; o.clr = A.clr; o.null_logl = A.nsum;
-    out[blockIdx.x] = o;
+    if (out) out[blockIdx.x] = o;
     if (clr_matrix) clr_matrix[t.dst] = A.clr;
   }
 #ifdef FSCL_TIMING
@@ -659,12 +664,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
 }
 
 void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
-                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s) {
+                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s, const int *n_tasks_dev) {
   if (n_tasks <= 0) return;
   if (flags & kFlagCount)
-    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix);
+    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev);
   else
-    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix);
+    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev);
 }
 
 // ---------------------------------------------------------------------------
@@ -676,7 +681,8 @@ void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &
 __global__ void __launch_bounds__(kPermThreads)
 permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, int *__restrict__ scratch_all,
                const int4 *__restrict__ blocks, const int *__restrict__ blk_start,
-               const int *__restrict__ blk_cnt) {
+               const int *__restrict__ blk_cnt, const int *__restrict__ skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;      // no active cell left: the round is a no-op
   const int slot = blockIdx.x;
   int *pc = pcls_all + (size_t)slot * n;
   int *sc = scratch_all + (size_t)slot * n;
@@ -714,7 +720,8 @@ __global__ void __launch_bounds__(kBucketThreads)
 bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stride,
               const int *__restrict__ pos, const double *__restrict__ null_tab, int *__restrict__ tkey_all,
               int *__restrict__ tpos_all, double *__restrict__ tnull_all, int *__restrict__ trun_all,
-              int *__restrict__ tnrun_all) {
+              int *__restrict__ tnrun_all, const int *__restrict__ skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;
   __shared__ unsigned keys[kTile];
   __shared__ double wsum[kBucketThreads / 32];
   __shared__ int hpos[kTile + 1];
@@ -789,17 +796,17 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
 }
 
 void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
-                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s) {
+                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s, const int *skip_if_zero) {
   if (n_slots <= 0) return;
   dim3 grid(n_pad / kTile, n_slots);
   bucket_kernel<<<grid, kBucketThreads, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, ts.key, ts.pos,
-                                          ts.tnull, ts.run, ts.nrun);
+                                          ts.tnull, ts.run, ts.nrun, skip_if_zero);
 }
 
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
-                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s) {
+                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s, const int *skip_if_zero) {
   if (n_slots <= 0) return;
-  permute_kernel<<<n_slots, kPermThreads, 0, s>>>(n, cls0, pcls_all, scratch_all, blocks, blk_start, blk_cnt);
+  permute_kernel<<<n_slots, kPermThreads, 0, s>>>(n, cls0, pcls_all, scratch_all, blocks, blk_start, blk_cnt, skip_if_zero);
 }
 
 // ---------------------------------------------------------------------------
@@ -832,8 +839,13 @@ __global__ void __launch_bounds__(32)
 gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ chr_end,
                   unsigned long long seed, const int *__restrict__ t_list, double nbp,
                   double width_bp, int4 *__restrict__ blocks, int stride,
-                  int *__restrict__ counts, int *__restrict__ flags, int *__restrict__ d7) {
+                  int *__restrict__ counts, int *__restrict__ flags, int *__restrict__ d7,
+                  const int *__restrict__ skip_if_zero) {
   const int slot = blockIdx.x, lane = threadIdx.x;
+  if (skip_if_zero && *skip_if_zero == 0) {
+    if (lane == 0) { counts[slot] = 0; flags[slot] = 0; d7[slot] = 0; }
+    return;
+  }
   const unsigned t = (unsigned)t_list[slot];
   int4 *out = blocks + (size_t)slot * stride;
   const unsigned full = 0xFFFFFFFFu, below = (1u << lane) - 1u;
@@ -843,7 +855,9 @@ gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ ch
     const unsigned b = base + (unsigned)lane;
     int j = (int)(dev_philox_draw(seed, t, 0, 2u * b) / (2147483647 + 1.0) * n);
     const double len = -1.0 / nbp * log(dev_philox_draw(seed, t, 0, 2u * b + 1u) / (2147483647 + 1.0));
-    const int lflag = (len < 2147483647.0 && fabs(len - rint(len)) <= 1e-9 * fmax(len, 1.0)) ? 2 : 0;
+    // device log() and the host's libm log() may differ in the last ulp, so (int)len can only differ when len
+    // lies within a few ulp of an integer: flag that (the host then redraws the round); 32 ulp of margin
+    const int lflag = (len < 2147483647.0 && fabs(len - rint(len)) <= 7.2e-15 * fmax(len, 1.0)) ? 2 : 0;
     int k = j + (len < 2147483647.0 ? (int)len : 0x3FFFFFFF);
     if (k < n && k >= 0) {
       const int lim = chr_end[j];
@@ -906,45 +920,59 @@ gen_blocks_kernel(int n, const int *__restrict__ pos, const int *__restrict__ ch
 
 void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,
                        double nbp, double width_bp, int4 *blocks, int stride, int *counts, int *flags, int *d7,
-                       int n_slots, cudaStream_t s) {
+                       int n_slots, cudaStream_t s, const int *skip_if_zero) {
   if (n_slots <= 0) return;
   gen_blocks_kernel<<<n_slots, 32, 0, s>>>(n, pos, chr_end, seed, t_list, nbp, width_bp, blocks, stride, counts,
-                                           flags, d7);
+                                           flags, d7, skip_if_zero);
 }
 
 // (permutation slot, active cell) -> search task; D4: the cell is re-derived from the observed
-// sweep position (scan-chromosome.c:481-486)
-__global__ void taskgen_kernel(int na, int ns, const int *__restrict__ active, const int *__restrict__ rows,
+// sweep position (scan-chromosome.c:481-486).  The active count lives on the device (count_dev): the
+// host sizes the launch from an older, larger count (na_cap) and never waits for the current one.
+// The round's CLR matrix is [ns][na] (this rank's permutations only), entry q * na + a.
+__global__ void taskgen_kernel(int na_cap, int ns, const int *__restrict__ active, const int *__restrict__ count_dev,
                                const int *__restrict__ pt_chr, const int *__restrict__ pt_sweep, int G,
-                               Task *__restrict__ tasks) {
+                               Task *__restrict__ tasks, int *__restrict__ n_tasks_dev,
+                               unsigned long long *__restrict__ task_total) {
+  const int na = min(*count_dev, na_cap);
   const int a = blockIdx.x * blockDim.x + threadIdx.x, q = blockIdx.y;
+  if (a == 0 && q == 0) { *n_tasks_dev = ns * na; atomicAdd(task_total, (unsigned long long)ns * (unsigned long long)na); }
   if (a >= na || q >= ns) return;
   const int s = active[a];
   const int sp = pt_sweep[s], start = sp - (sp % G);
-  tasks[(size_t)q * na + a] = Task{q, pt_chr[s], start, start + G, (int)((size_t)rows[q] * na + a)};
+  tasks[(size_t)q * na + a] = Task{q, pt_chr[s], start, start + G, (int)((size_t)q * na + a)};
 }
 
-void launch_taskgen(int na, int ns, const int *active, const int *rows, const int *pt_chr, const int *pt_sweep,
-                    int G, Task *tasks, cudaStream_t s) {
-  if (na <= 0 || ns <= 0) return;
-  dim3 grid((na + 255) / 256, ns);
-  taskgen_kernel<<<grid, 256, 0, s>>>(na, ns, active, rows, pt_chr, pt_sweep, G, tasks);
+void launch_taskgen(int na_cap, int ns, const int *active, const int *count_dev, const int *pt_chr, const int *pt_sweep,
+                    int G, Task *tasks, int *n_tasks_dev, unsigned long long *task_total, cudaStream_t s) {
+  if (na_cap <= 0 || ns <= 0) return;
+  dim3 grid((na_cap + 255) / 256, ns);
+  taskgen_kernel<<<grid, 256, 0, s>>>(na_cap, ns, active, count_dev, pt_chr, pt_sweep, G, tasks, n_tasks_dev, task_total);
 }
 
 // Counting + stochastic pruning of a round, one thread per active cell, rows in permutation
 // order (scan-chromosome.c:488-498; D5, D6).  The pruning uniform is Philox(t, stream 1, cell).
-__global__ void replay_kernel(int na, int R, int t_first, const int *__restrict__ active,
-                              const double *__restrict__ matrix, const double *__restrict__ obs_clr,
-                              int *__restrict__ pp, int *__restrict__ pn, int *__restrict__ pf,
-                              float *__restrict__ permute_clr, unsigned long long seed, int prune,
-                              int *__restrict__ scored) {
+// Permutation t of the round was scored by rank t % stride as its local row q (the q-th of its
+// permutations inside the round); after the all-gather rank g's rows sit at matrix + g * chunk,
+// laid out [q][na].  One GPU: stride 1, chunk 0.  permute_clr = [cell][clr_cap] (first clr_cap
+// permuted CLRs as float, scan-chromosome.c:496-497 with CLR_NULL_DIST_SAVE capped at the test's length).
+__global__ void replay_kernel(int na_cap, const int *__restrict__ count_dev, int R, int t_first, int stride,
+                              size_t chunk, const int *__restrict__ active, const double *__restrict__ matrix,
+                              const double *__restrict__ obs_clr, int *__restrict__ pp, int *__restrict__ pn,
+                              int *__restrict__ pf, float *__restrict__ permute_clr, int clr_cap,
+                              unsigned long long seed, int prune, int *__restrict__ scored) {
+  const int na = min(*count_dev, na_cap);
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= na) return;
   const int s = active[a];
   const double obs = obs_clr[s];
   int p = pp[s], n = pn[s], fin = 0;
+  const int t0m = t_first % stride;
   for (int r = 0; r < R && !fin; r++) {
-    const double clr = matrix[(size_t)r * na + a];
+    const int g = (t0m + r) % stride;
+    const int first_r = (g - t0m + stride) % stride;       // first row of the round that rank g scored
+    const int q = (r - first_r) / stride;
+    const double clr = matrix[(size_t)g * chunk + (size_t)q * na + a];
     if (scored[r] == 0) scored[r] = 1;                 // benign race: every writer stores 1
     if (clr >= obs) {
       p++;
@@ -953,26 +981,30 @@ __global__ void replay_kernel(int na, int R, int t_first, const int *__restrict_
         if (p / (double)n >= u / (2147483647 + 1.0)) fin = 1;
       }
     }
-    if (permute_clr && n < 10000) permute_clr[(size_t)s * 10000 + n] = (float)clr;
+    if (permute_clr && n < clr_cap) permute_clr[(size_t)s * clr_cap + n] = (float)clr;
     n++;
   }
   pp[s] = p; pn[s] = n; pf[s] = fin;
 }
 
-void launch_replay(int na, int R, int t_first, const int *active, const double *matrix, const double *obs_clr,
-                   int *pp, int *pn, int *pf, float *permute_clr, unsigned long long seed, int prune, int *scored,
-                   cudaStream_t s) {
-  if (na <= 0 || R <= 0) return;
-  replay_kernel<<<(na + 255) / 256, 256, 0, s>>>(na, R, t_first, active, matrix, obs_clr, pp, pn, pf, permute_clr,
-                                                 seed, prune, scored);
+void launch_replay(int na_cap, const int *count_dev, int R, int t_first, int stride, size_t chunk, const int *active,
+                   const double *matrix, const double *obs_clr, int *pp, int *pn, int *pf, float *permute_clr,
+                   int clr_cap, unsigned long long seed, int prune, int *scored, cudaStream_t s) {
+  if (na_cap <= 0 || R <= 0) return;
+  replay_kernel<<<(na_cap + 255) / 256, 256, 0, s>>>(na_cap, count_dev, R, t_first, stride, chunk, active, matrix, obs_clr,
+                                                     pp, pn, pf, permute_clr, clr_cap, seed, prune, scored);
 }
 
-// Order-preserving compaction of the active list (scan-chromosome.c:446-457): one CTA.
-__global__ void __launch_bounds__(1024) compact_kernel(int na, const int *__restrict__ active_in,
+// Order-preserving compaction of the active list (scan-chromosome.c:446-457): one CTA.  Also folds the
+// round's "permutation scored" flags into the running total and clears them for the next round.
+__global__ void __launch_bounds__(1024) compact_kernel(int na_cap, const int *__restrict__ count_in,
+                                                       const int *__restrict__ active_in,
                                                        const int *__restrict__ pf, int *__restrict__ active_out,
-                                                       int *__restrict__ count_out) {
+                                                       int *__restrict__ count_out, int *__restrict__ scored, int R,
+                                                       unsigned long long *__restrict__ scored_total) {
   __shared__ int wsum[32];
   __shared__ int base;
+  const int na = min(*count_in, na_cap);
   if (threadIdx.x == 0) base = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -990,11 +1022,64 @@ __global__ void __launch_bounds__(1024) compact_kernel(int na, const int *__rest
     if (threadIdx.x == 0) { int tot = 0; for (int w = 0; w < 32; w++) tot += wsum[w]; base += tot; }
     __syncthreads();
   }
-  if (threadIdx.x == 0) *count_out = base;
+  if (threadIdx.x == 0) {
+    *count_out = base;
+    int ns = 0;
+    for (int r = 0; r < R; r++) { ns += scored[r]; scored[r] = 0; }
+    if (ns) atomicAdd(scored_total, (unsigned long long)ns);
+  }
 }
 
-void launch_compact(int na, const int *active_in, const int *pf, int *active_out, int *count_out, cudaStream_t s) {
-  compact_kernel<<<1, 1024, 0, s>>>(na, active_in, pf, active_out, count_out);
+void launch_compact(int na_cap, const int *count_in, const int *active_in, const int *pf, int *active_out,
+                    int *count_out, int *scored, int R, unsigned long long *scored_total, cudaStream_t s) {
+  compact_kernel<<<1, 1024, 0, s>>>(na_cap, count_in, active_in, pf, active_out, count_out, scored, R, scored_total);
+}
+
+// Stored permuted CLRs between the device table [cell][clr_cap] and one packed buffer (cell i at
+// off[i], min(pn[i], clr_cap) values): one kernel + one copy instead of a copy per cell.
+__global__ void pack_clr_kernel(int n_pts, const int *__restrict__ pn, const long long *__restrict__ off, int clr_cap,
+                                float *__restrict__ table, float *__restrict__ packed, int to_table) {
+  const int i = blockIdx.x;
+  if (i >= n_pts) return;
+  const int m = min(pn[i], clr_cap);
+  float *row = table + (size_t)i * clr_cap, *dst = packed + off[i];
+  for (int k = threadIdx.x; k < m; k += blockDim.x) {
+    if (to_table) row[k] = dst[k]; else dst[k] = row[k];
+  }
+}
+
+void launch_pack_clr(int n_pts, const int *pn, const long long *off, int clr_cap, float *table, float *packed,
+                     int to_table, cudaStream_t s) {
+  if (n_pts <= 0) return;
+  pack_clr_kernel<<<n_pts, 128, 0, s>>>(n_pts, pn, off, clr_cap, table, packed, to_table);
+}
+
+// p-value projection (README.md:11 of the reference, never implemented there): one warp per
+// cell; lambda = max(mean of the stored permuted CLRs - df, 0), p = P[ncx2(df, lambda) >= CLR_obs].
+__global__ void __launch_bounds__(128) project_kernel(int n_pts, const int *__restrict__ pn,
+                                                      const double *__restrict__ obs_clr,
+                                                      const float *__restrict__ table, int clr_cap, double df,
+                                                      double *__restrict__ lambda_out, double *__restrict__ p_out) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n_pts) return;
+  const int m = min(pn[i], clr_cap);
+  const float *row = table + (size_t)i * clr_cap;
+  double v = 0.0;
+  for (int k = lane; k < m; k += 32) v += (double)row[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  if (lane == 0) {
+    const double mean = m > 0 ? v / m : 0.0;
+    const double lambda = fmax(mean - df, 0.0);
+    if (lambda_out) lambda_out[i] = lambda;
+    p_out[i] = m > 0 ? ncx2_sf(obs_clr[i], df, lambda) : 1.0;
+  }
+}
+
+void launch_project(int n_pts, const int *pn, const double *obs_clr, const float *table, int clr_cap, double df,
+                    double *lambda_out, double *p_out, cudaStream_t s) {
+  if (n_pts <= 0) return;
+  project_kernel<<<(n_pts + 3) / 4, 128, 0, s>>>(n_pts, pn, obs_clr, table, clr_cap, df, lambda_out, p_out);
 }
 
 // ---------------------------------------------------------------------------

@@ -98,20 +98,28 @@ struct AlphaTables {
 void upload_alpha_tables(const AlphaTables &t);
 
 void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
-                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s);
+                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s,
+                 const int *n_tasks_dev = nullptr);
 void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
-                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s);
+                   const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s,
+                   const int *skip_if_zero = nullptr);
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,
-                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s);
+                    const int *blk_start, const int *blk_cnt, int n_slots, cudaStream_t s,
+                    const int *skip_if_zero = nullptr);
 void launch_gen_blocks(int n, const int *pos, const int *chr_end, unsigned long long seed, const int *t_list,
                        double nbp, double width_bp, int4 *blocks, int stride, int *counts, int *flags, int *d7,
-                       int n_slots, cudaStream_t s);
-void launch_taskgen(int na, int ns, const int *active, const int *rows, const int *pt_chr, const int *pt_sweep,
-                    int G, Task *tasks, cudaStream_t s);
-void launch_replay(int na, int R, int t_first, const int *active, const double *matrix, const double *obs_clr,
-                   int *pp, int *pn, int *pf, float *permute_clr, unsigned long long seed, int prune, int *scored,
-                   cudaStream_t s);
-void launch_compact(int na, const int *active_in, const int *pf, int *active_out, int *count_out, cudaStream_t s);
+                       int n_slots, cudaStream_t s, const int *skip_if_zero = nullptr);
+void launch_taskgen(int na_cap, int ns, const int *active, const int *count_dev, const int *pt_chr, const int *pt_sweep,
+                    int G, Task *tasks, int *n_tasks_dev, unsigned long long *task_total, cudaStream_t s);
+void launch_replay(int na_cap, const int *count_dev, int R, int t_first, int stride, size_t chunk, const int *active,
+                   const double *matrix, const double *obs_clr, int *pp, int *pn, int *pf, float *permute_clr,
+                   int clr_cap, unsigned long long seed, int prune, int *scored, cudaStream_t s);
+void launch_compact(int na_cap, const int *count_in, const int *active_in, const int *pf, int *active_out,
+                    int *count_out, int *scored, int R, unsigned long long *scored_total, cudaStream_t s);
+void launch_pack_clr(int n_pts, const int *pn, const long long *off, int clr_cap, float *table, float *packed,
+                     int to_table, cudaStream_t s);
+void launch_project(int n_pts, const int *pn, const double *obs_clr, const float *table, int clr_cap, double df,
+                    double *lambda_out, double *p_out, cudaStream_t s);
 void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);
 
 enum { kFlagSingle = 1,      // evaluate start_pos only (search_maxalpha at a point)

@@ -79,6 +79,8 @@ typedef struct {
   int32_t first_perm;       /* sharding: score permutations t with t % perm_stride == first_perm */
   int32_t perm_stride;      /* 1 on a single GPU */
   int32_t round_perms;      /* 0 = auto */
+  int32_t save_clr;         /* 1 = keep the permuted CLRs on the device (fscl_perm_fetch_clr, fscl_perm_project)
+                               even when no dense permute_clr buffer is given */
 } fscl_permute_opts_t;
 
 typedef struct {
@@ -146,6 +148,29 @@ int fscl_perm_snapshot(void *ctx, int32_t *t_next_out);
  * and stored CLRs found in pts / permute_clr (a checkpoint).  Counter-based stream only: the
  * result equals an uninterrupted run bit for bit. */
 int fscl_perm_seek(void *ctx, int32_t t_next);
+/* Stored permuted CLRs (scan_pt_t.permute_clr, scan-chromosome.c:496-497) without the 40 KB-per-cell dense
+ * table of the reference: after fscl_perm_end / fscl_perm_snapshot of a test begun with
+ * permute_clr != NULL or opts.save_clr, cell i holds offsets[i+1] - offsets[i] = min(permute_n, FSCL_NULL_SAVE)
+ * values at packed + offsets[i].  packed == NULL fills offsets[n_pts + 1] only.  One gather kernel + one copy. */
+int fscl_perm_fetch_clr(void *ctx, int64_t *offsets, float *packed, int64_t cap);
+/* Projected p-values (README.md:11 of the reference; never implemented there -- definition in DESIGN.md 3.6)
+ * computed on the device from the CLRs kept there: lambda = max(mean - df, 0), p = P[ncx2(df, lambda) >= clr]. */
+int fscl_perm_project(void *ctx, double df, double *lambda_out, double *p_out);
+/* Multi-GPU (the intent of fscl-master.c:1-18).  A context with a communicator shards
+ * fscl_scan_chromosome over cells and fscl_scan_permute / the round API over permutations
+ * (rank g scores t = g mod world; one ncclAllGather of the round's CLR rows per round on the library's
+ * stream; every rank replays the same counting rule, so results are identical on all ranks and equal to
+ * the single-GPU ones).  Every rank must make the same calls with the same arguments.
+ *   one process per GPU : rank 0 calls fscl_comm_unique_id, ships the 128 bytes to the others (any
+ *                         channel), every rank calls fscl_comm_init_rank;
+ *   one process, n GPUs : fscl_comm_init_all on n contexts (one per device), then one host thread per
+ *                         context.
+ * libnccl.so.2 is loaded on first use (FSCL_B200_NCCL overrides the path). */
+int fscl_comm_unique_id(char *id128);
+int fscl_comm_init_rank(void *ctx, int world, int rank, const char *id128);
+int fscl_comm_init_all(void **ctxs, int n);
+int fscl_comm_destroy(void *ctx);
+int fscl_comm_info(void *ctx, int *world, int *rank);
 /* Host-side pieces of the path, callable without a device (same code the GPU
  * path runs on the host): alpha candidate tables [12][15] (row 11 = coarse list,
  * sm-search.c:276-296, with the per-alpha distance cut), cell enumeration, the

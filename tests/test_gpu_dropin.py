@@ -1,5 +1,5 @@
 """Drop-in proof on the GPU: (1) the reference's unmodified main() + host objects
-linked against libfscl_dropin.so (oracle/_ref/fscl_dropin_exe) reproduce the
+linked against libfscl_dropin.so (fscl_b200/_host/fscl_gpu) reproduce the
 golden outputs of the unmodified reference executable byte for byte, permutation
 columns included (same libc rand() stream); (2) the Python host layer does the same."""
 import gzip
@@ -13,13 +13,13 @@ from tests.test_golden import GOLD, INDEX, load_case
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXE = os.path.join(ROOT, "oracle", "_ref", "fscl_dropin_exe")
+EXE = os.path.join(ROOT, "fscl_b200", "_host", "fscl_gpu")
 
 
 @pytest.mark.parametrize("name", sorted(INDEX))
 def test_reference_main_on_gpu_dropin_matches_golden(built, name, tmp_path):
     if not os.path.exists(EXE):
-        pytest.fail("oracle/_ref/fscl_dropin_exe missing: run build() where /root/reference exists")
+        pytest.fail("fscl_b200/_host/fscl_gpu missing: run build() where /root/reference exists")
     inp, out = str(tmp_path / "in.snps"), str(tmp_path / "out.txt")
     open(inp, "w").write(gzip.open(os.path.join(GOLD, name + ".snps.gz"), "rt").read())
     cmd = [EXE, "-f", inp, "-o", out, "--n-threads=1", *INDEX[name]["args"]]

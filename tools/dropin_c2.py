@@ -1,10 +1,10 @@
-"""The reference's own main() linked against the drop-in (oracle/_ref/fscl_dropin_exe) on c2 with 1000 permutations:
+"""The reference's own main() linked against the drop-in (fscl_b200/_host/fscl_gpu) on c2 with 1000 permutations:
 wall time of the whole command line, counter-based stream and the reference's rand() stream."""
 import os, subprocess, sys, tempfile, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fscl_b200 import synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-exe = os.path.join(ROOT, "oracle", "_ref", "fscl_dropin_exe")
+exe = os.path.join(ROOT, "fscl_b200", "_host", "fscl_gpu")
 tab, opt = synth.config2()
 d = tempfile.mkdtemp()
 inp = os.path.join(d, "c2.snps")

@@ -71,7 +71,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
            "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima",
            "fscl_perm_fetch_clr", "fscl_perm_project", "fscl_comm_unique_id", "fscl_comm_init_rank", "fscl_comm_init_all",
-           "fscl_comm_destroy", "fscl_comm_info"]
+           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move"]
 
 _lib = None
 
@@ -125,6 +125,7 @@ def load_library(path=LIB_PATH):
     L.fscl_comm_init_all.argtypes = [vp, ci]
     L.fscl_comm_destroy.argtypes = [vp]
     L.fscl_comm_info.argtypes = [vp, vp, vp]
+    L.fscl_comm_move.argtypes = [vp, vp]
     _lib = L
     return L
 
@@ -426,6 +427,10 @@ class Scanner:
         round inside the library); every rank must make the same calls and gets identical results."""
         buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
         _check(self.L.fscl_comm_init_rank(self._ctx, world, rank, buf))
+
+    def comm_take(self, other):
+        """Adopt the communicator of another Scanner on the same device (it is left without one)."""
+        _check(self.L.fscl_comm_move(self._ctx, other._ctx))
 
     def comm_info(self):
         w, r = C.c_int(1), C.c_int(0)

@@ -1584,6 +1584,20 @@ extern "C" int fscl_comm_destroy(void *ctx) {
   return FSCL_OK;
 }
 
+// hand the communicator of one context to another context on the same device (a fresh problem on the
+// same rank does not need a fresh NCCL bootstrap); src is left without one
+extern "C" int fscl_comm_move(void *dst_ctx, void *src_ctx) {
+  Ctx *d = (Ctx *)dst_ctx, *s = (Ctx *)src_ctx;
+  if (!d || !s || d == s) return fail(FSCL_ERR_ARG, "bad argument");
+  if (d->comm) return fail(FSCL_ERR_ARG, "destination already has a communicator");
+  if (d->device != s->device) return fail(FSCL_ERR_ARG, "contexts are on different devices");
+  CK(cudaSetDevice(s->device));
+  CK(cudaStreamSynchronize(s->stream));
+  d->comm = s->comm; d->world = s->world; d->rank = s->rank;
+  s->comm = nullptr; s->world = 1; s->rank = 0;
+  return FSCL_OK;
+}
+
 extern "C" int fscl_comm_info(void *ctx, int *world, int *rank) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(FSCL_ERR_ARG, "bad argument");

@@ -170,6 +170,7 @@ int fscl_comm_unique_id(char *id128);
 int fscl_comm_init_rank(void *ctx, int world, int rank, const char *id128);
 int fscl_comm_init_all(void **ctxs, int n);
 int fscl_comm_destroy(void *ctx);
+int fscl_comm_move(void *dst_ctx, void *src_ctx);   /* same device: a new problem on the same rank keeps the communicator */
 int fscl_comm_info(void *ctx, int *world, int *rank);
 /* Host-side pieces of the path, callable without a device (same code the GPU
  * path runs on the host): alpha candidate tables [12][15] (row 11 = coarse list,

@@ -71,7 +71,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
            "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima",
            "fscl_perm_fetch_clr", "fscl_perm_project", "fscl_comm_unique_id", "fscl_comm_init_rank", "fscl_comm_init_all",
-           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move"]
+           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move", "fscl_debug_histogram"]
 
 _lib = None
 
@@ -106,6 +106,7 @@ def load_library(path=LIB_PATH):
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_set_exact_candidates.argtypes = [vp, ci]
     L.fscl_debug_counters.argtypes = [vp, vp]
+    L.fscl_debug_histogram.argtypes = [vp, vp]
     L.fscl_reset_stats.argtypes = [vp]
     L.fscl_fp64_peak.argtypes = [ci, vp]
     L.fscl_device_gen_blocks.argtypes = [vp, vp, ci, vp, ci, vp]

@@ -241,6 +241,7 @@ struct Ctx {
   fscl_stats_t stats{};
 };
 
+constexpr int kDebugCounters = 16 + 128;                // see fscl_debug_counters
 constexpr int kPinSlots = 1024;                    // permutations per rank and round the pinned flag area holds
 
 struct SlotRef {
@@ -659,10 +660,10 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   CK(cudaMemcpy(c->d_tile_hi, thi.data(), sizeof(int) * n_tiles, cudaMemcpyHostToDevice));
   CK(dev_malloc(&c->d_logT, sizeof(double) * 65536));
   CK(dev_malloc(&c->d_null, sizeof(double) * NC));
-  CK(dev_malloc(&c->d_terms, 16 * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
+  CK(dev_malloc(&c->d_terms, kDebugCounters * sizeof(unsigned long long)));   // [0] SNP-terms (COUNT launches), [1] coarse passes repeated exactly
   CK(dev_malloc(&c->d_chr_end, sizeof(int) * c->n));
   CK(cudaMemcpy(c->d_chr_end, c->chr_end_index.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
-  CK(cudaMemset(c->d_terms, 0, 16 * sizeof(unsigned long long)));
+  CK(cudaMemset(c->d_terms, 0, kDebugCounters * sizeof(unsigned long long)));
   CK(cudaMemcpy(c->d_pos, c->h_pos.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cls0, c->h_cls.data(), sizeof(int) * c->n, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_chr_start, c->chr_start.data(), sizeof(int) * c->n_chr, cudaMemcpyHostToDevice));
@@ -948,7 +949,11 @@ constexpr size_t kSlotMemory = (size_t)12 << 30;      // device memory the two s
 
 static int engine_resources(Ctx *c) {
   if (c->prep) return FSCL_OK;
-  CK(cudaStreamCreateWithFlags(&c->prep, cudaStreamNonBlocking));
+  // highest priority: its few, short kernels must slip in between the CTAs of the running scan instead of
+  // queueing behind that whole grid (equal priorities serialise prep(r) after scan(r-1): measured)
+  int prio_lo = 0, prio_hi = 0;
+  CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CK(cudaStreamCreateWithPriority(&c->prep, cudaStreamNonBlocking, prio_hi));
   for (int k = 0; k < 2; k++) {
     CK(cudaEventCreateWithFlags(&c->ev_gen[k], cudaEventDisableTiming | cudaEventBlockingSync));
     CK(cudaEventCreateWithFlags(&c->ev_prep[k], cudaEventDisableTiming));
@@ -1827,6 +1832,17 @@ extern "C" int fscl_debug_counters(void *ctx, unsigned long long *out16) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(out16, c->d_terms, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return FSCL_OK;
+}
+
+// -DFSCL_HIST builds: SNP-terms of the COUNT launches by [pass: coarse, fine][path: direct, covering, crossing,
+// behind-a-bound][candidate 0..15] (tools/probe_terms.py)
+extern "C" int fscl_debug_histogram(void *ctx, unsigned long long *out128) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c || !out128) return fail(FSCL_ERR_ARG, "bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaMemcpy(out128, c->d_terms + 16, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return FSCL_OK;
 }
 

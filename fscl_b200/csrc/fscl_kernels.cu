@@ -154,7 +154,16 @@ struct PhaseScratch {
 #ifdef FSCL_TIMING
   long long tacc[16], tlast;            // phase latencies seen by thread 0 (debug builds only)
 #endif
+#ifdef FSCL_HIST
+  unsigned long long hist[2][4][16];    // COUNT launches of debug builds: SNP-terms by pass, code path, candidate
+#endif
 };
+
+#ifdef FSCL_HIST
+#define FSCL_HADD(W, cat, j, n) do { if (COUNT) atomicAdd(&(W).hist[WITHN ? 0 : 1][cat][j], (unsigned long long)(n)); } while (0)
+#else
+#define FSCL_HADD(W, cat, j, n) do { } while (0)
+#endif
 
 #ifdef FSCL_TIMING
 #define FSCL_TICK(W, slot) do { if (threadIdx.x == 0) { const long long now_ = clock64(); (W).tacc[slot] += now_ - (W).tlast; (W).tlast = now_; } } while (0)
@@ -322,6 +331,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
             ld_row(reinterpret_cast<const double *>(cr + (unsigned long long)k * 32ull), c0, c1, c2, c3);
             acc[j] += fma(x, fma(x, fma(x, c0, c1), c2), c3);
             if (COUNT) nterms += 1ull;
+            FSCL_HADD(W, 0, j, 1);
           }
         }
       }
@@ -450,6 +460,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           if (j >= jfull) break;
           batch_terms_pipelined<1, kB>(acc + j, c_alpha.la[row] + j, x0, crow, inv_step, offm);
           if (COUNT) nterms += (unsigned long long)kB;
+          FSCL_HADD(W, 3, j, kB);
         }
       } else if (jfull > 0 && jfull <= 4) {
         // far tiles: at most four alphas, rows double-buffered across the records of the batch
@@ -458,6 +469,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         else if (jfull == 2) batch_terms_pipelined<2, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
         else batch_terms_pipelined<1, kB>(acc, c_alpha.la[row], x0, crow, inv_step, offm);
         if (COUNT) nterms += (unsigned long long)(jfull * kB);
+        for (int j = 0; j < jfull; j++) FSCL_HADD(W, 1, j, kB);
       } else if (jfull > 4) {
         // near tiles: groups of four candidates, each double-buffered across the records of the batch
 #pragma unroll
@@ -470,6 +482,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           else batch_terms_pipelined<1, kB>(acc + g, c_alpha.la[row] + g, x0, crow, inv_step, offm);
         }
         if (COUNT) nterms += (unsigned long long)(jfull * kB);
+        for (int j = 0; j < jfull; j++) FSCL_HADD(W, 1, j, kB);
       }
       // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate;
       // the rows of the kB records of a candidate are in flight together
@@ -498,6 +511,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
             const bool inc = dq[u] <= dm;
             if (inc) acc[j] += y;
             if (COUNT) nterms += inc ? 1ull : 0ull;
+            FSCL_HADD(W, 2, j, inc ? 1 : 0);
           }
         }
       }
@@ -578,6 +592,9 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   if (threadIdx.x == 0) { for (int q = 0; q < 16; q++) W.tacc[q] = 0; W.tlast = clock64(); }
 #endif
   if (threadIdx.x == 0) W.bmF = 0;
+#ifdef FSCL_HIST
+  for (int q = threadIdx.x; q < 128; q += kScanThreads) (&W.hist[0][0][0])[q] = 0ull;
+#endif
   if (prune) {
     // bounds of the far tiles, once for every position the search of this cell can visit
     if (threadIdx.x < 32) {
@@ -656,6 +673,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   if (threadIdx.x == 0)
     for (int q = 0; q < 14; q++) atomicAdd(term_counter + 2 + q, (unsigned long long)W.tacc[q]);
 #endif
+#ifdef FSCL_HIST
+  __syncthreads();
+  if (COUNT)
+    for (int q = threadIdx.x; q < 128; q += kScanThreads)
+      if ((&W.hist[0][0][0])[q]) atomicAdd(term_counter + 16 + q, (&W.hist[0][0][0])[q]);
+#endif
   if (COUNT) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nterms += __shfl_xor_sync(0xFFFFFFFFu, nterms, o);
@@ -712,9 +735,19 @@ permute_kernel(int n, const int *__restrict__ cls0, int *__restrict__ pcls_all, 
 
 // ---------------------------------------------------------------------------
 // Class-bucketing of one genome instance: every tile of kTile consecutive sites
-// is sorted by (class, index) with a shared-memory bitonic network; the record
-// is key = class | index_in_tile << 20 plus the site's position.
-constexpr int kBucketThreads = kTile / 2 < 1024 ? kTile / 2 : 1024;
+// is sorted by (class, index); the record is key = class | index_in_tile << 20 plus the site's position.
+// Bitonic network with 8 keys per thread held in registers: the strides 1, 2, 4 are compare-exchanges
+// inside a thread, the strides 8 .. 128 warp shuffles, and only the strides >= 256 (three of the 55
+// steps of a 1024-key network) go through shared memory (the round-1 kernel synchronised the CTA after
+// every step; this one is the per-permutation floor of the late rounds of a pruned test).
+constexpr int kBucketKeys = 8;
+constexpr int kBucketThreads = kTile / kBucketKeys;
+static_assert(kBucketThreads % 32 == 0 && kBucketThreads <= 1024, "tile must be a multiple of 256 sites");
+
+__device__ __forceinline__ void bucket_cx(unsigned &a, unsigned &b, bool up) {
+  const unsigned lo = min(a, b), hi = max(a, b);
+  a = up ? lo : hi; b = up ? hi : lo;
+}
 
 __global__ void __launch_bounds__(kBucketThreads)
 bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stride,
@@ -729,21 +762,49 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
   const int tile = blockIdx.x, slot = blockIdx.y;
   const int *cls = cls_all + (size_t)slot * cls_stride;
   const int base = tile * kTile;
-  for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
-    const int gi = base + e;
-    keys[e] = ((gi < n ? (unsigned)cls[gi] : 0u) << 12) | (unsigned)e;
+  const int t = threadIdx.x, p0 = t * kBucketKeys;        // this thread holds positions p0 .. p0 + 7
+  unsigned v[kBucketKeys];
+#pragma unroll
+  for (int r = 0; r < kBucketKeys; r++) {
+    const int gi = base + p0 + r;
+    v[r] = ((gi < n ? (unsigned)cls[gi] : 0u) << 12) | (unsigned)(p0 + r);
+  }
+#pragma unroll 1
+  for (int k = 2; k <= kTile; k <<= 1) {
+#pragma unroll 1
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= kBucketKeys * 32) {
+        // partner in another warp: through shared memory
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kBucketKeys; r++) keys[p0 + r] = v[r];
+        __syncthreads();
+        const bool lower = (p0 & j) == 0, up = (p0 & k) == 0;
+#pragma unroll
+        for (int r = 0; r < kBucketKeys; r++) {
+          const unsigned o = keys[(p0 ^ j) + r];
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      } else if (j >= kBucketKeys) {
+        const bool lower = (p0 & j) == 0, up = (p0 & k) == 0;
+        const int lm = j / kBucketKeys;
+#pragma unroll
+        for (int r = 0; r < kBucketKeys; r++) {
+          const unsigned o = __shfl_xor_sync(0xFFFFFFFFu, v[r], lm);
+          v[r] = (lower == up) ? min(v[r], o) : max(v[r], o);
+        }
+      } else {
+        // inside the thread; the direction bit k can be one of the low bits here (k <= 8)
+#pragma unroll
+        for (int r = 0; r < kBucketKeys; r++)
+          if ((r & j) == 0) bucket_cx(v[r], v[r | j], ((p0 + r) & k) == 0);
+      }
+    }
   }
   __syncthreads();
-  for (int k = 2; k <= kTile; k <<= 1)
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < kTile / 2; t += kBucketThreads) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;
-        const bool up = (lo & k) == 0;
-        const unsigned a = keys[lo], b = keys[hi];
-        if ((a > b) == up) { keys[lo] = b; keys[hi] = a; }
-      }
-      __syncthreads();
-    }
+#pragma unroll
+  for (int r = 0; r < kBucketKeys; r++) keys[p0 + r] = v[r];
+  __syncthreads();
   int *tkey = tkey_all + (size_t)slot * n_pad, *tpos = tpos_all + (size_t)slot * n_pad;
   for (int e = threadIdx.x; e < kTile; e += kBucketThreads) {
     const unsigned kk = keys[e];
@@ -781,12 +842,12 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
     if (threadIdx.x == 0) tnrun_all[(size_t)slot * (n_pad / kTile) + tile] = nrun;
   }
   // null log-likelihood of the tile (fixed tree; only complete tiles are ever read)
-  double v = 0.0;
+  double nsum = 0.0;
   for (int e = threadIdx.x; e < kTile; e += kBucketThreads)
-    if (base + e < n) v += __ldg(null_tab + cls[base + e]);
+    if (base + e < n) nsum += __ldg(null_tab + cls[base + e]);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  for (int o = 16; o > 0; o >>= 1) nsum += __shfl_xor_sync(0xFFFFFFFFu, nsum, o);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = nsum;
   __syncthreads();
   if (threadIdx.x == 0) {
     double tsum = 0.0;

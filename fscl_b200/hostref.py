@@ -13,6 +13,7 @@ Nothing here imports ``oracle/``.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import tempfile
 
@@ -61,6 +62,15 @@ class sm_ptable_t(C.Structure):
 
 
 _lib = None
+
+
+def _libm_log(x):
+    """log() of the C library, as compute_snp_null_model calls it (scan-chromosome.c:31-34); numpy's vectorised
+    log differs in the last ulp on some CPUs"""
+    x = float(x)
+    if x > 0.0:
+        return math.log(x)
+    return -math.inf if x == 0.0 else math.nan
 
 
 def load_library(path=HOSTREF_SO):
@@ -162,14 +172,13 @@ def load_problem(snp_file=None, table=None, ms_file=None, ms_segment_length=0, m
         for d in range(s.n_depths):
             n = int(depths[d])
             t = sm_p[d]
-            with np.errstate(divide="ignore"):
-                for f in range(n + 1):
-                    coef[base[d] + f] = np.ctypeslib.as_array(t.spline_func[f].contents.coef[0], shape=(K, 4))
-                    null_tab[base[d] + f] = np.log(fsp[d][f])                                # scan-chromosome.c:23-37
-                for f in range(n // 2 + 1):
-                    coef[base[d] + n + 1 + f] = np.ctypeslib.as_array(t.fspline_func[f].contents.coef[0], shape=(K, 4))
-                    null_tab[base[d] + n + 1 + f] = (np.log(fsp[d][f] + fsp[d][n - f]) if f != n - f
-                                                     else np.log(fsp[d][f]))
+            for f in range(n + 1):
+                coef[base[d] + f] = np.ctypeslib.as_array(t.spline_func[f].contents.coef[0], shape=(K, 4))
+                null_tab[base[d] + f] = _libm_log(fsp[d][f])                                 # scan-chromosome.c:23-37
+            for f in range(n // 2 + 1):
+                coef[base[d] + n + 1 + f] = np.ctypeslib.as_array(t.fspline_func[f].contents.coef[0], shape=(K, 4))
+                null_tab[base[d] + n + 1 + f] = (_libm_log(fsp[d][f] + fsp[d][n - f]) if f != n - f
+                                                 else _libm_log(fsp[d][f]))
     buf = (C.c_char * (32 * s.n_snps)).from_address(C.addressof(s.snps.contents))
     snps = np.frombuffer(buf, dtype=SNP_DTYPE)
     cls = np.where(snps["folded"] != 0,

@@ -216,6 +216,8 @@ int fscl_set_exact_candidates(void *ctx, int on);
 /* Debug hook: the 16 device counters of the context ([0] SNP-terms of COUNT launches, [1] coarse passes
  * repeated exactly; [2..15] phase latencies in cycles, only filled by a library built with -DFSCL_TIMING). */
 int fscl_debug_counters(void *ctx, unsigned long long *out16);
+/* Libraries built with -DFSCL_HIST: SNP-terms of the term-counting launches by [pass][code path][candidate] (128 values). */
+int fscl_debug_histogram(void *ctx, unsigned long long *out128);
 int fscl_get_stats(void *ctx, fscl_stats_t *stats);
 int fscl_reset_stats(void *ctx);
 /* FP64 FMA peak of the device (dependent-chain microbenchmark), in TFLOP/s */

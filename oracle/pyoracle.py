@@ -14,6 +14,7 @@ does.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 import tempfile
@@ -90,6 +91,15 @@ def libc():
         _libc.srand.argtypes = [C.c_uint]
         _libc.rand.restype = C.c_int
     return _libc
+
+
+def _libm_log(x):
+    """log() of the C library, as compute_snp_null_model calls it (numpy's vectorised log differs in the last
+    ulp on some CPUs)."""
+    x = float(x)
+    if x > 0.0:
+        return math.log(x)
+    return -math.inf if x == 0.0 else math.nan
 
 
 def ref_available():
@@ -194,13 +204,11 @@ class RefProblem:
             for f in range(n + 1):
                 sp = t.spline_func[f].contents
                 coef[base[d] + f] = np.ctypeslib.as_array(sp.coef[0], shape=(K, 4))
-                with np.errstate(divide="ignore"):
-                    null_tab[base[d] + f] = np.log(fsp[f])
+                null_tab[base[d] + f] = _libm_log(fsp[f])
             for f in range(n // 2 + 1):
                 sp = t.fspline_func[f].contents
                 coef[base[d] + n + 1 + f] = np.ctypeslib.as_array(sp.coef[0], shape=(K, 4))
-                with np.errstate(divide="ignore"):
-                    null_tab[base[d] + n + 1 + f] = np.log(fsp[f] + fsp[n - f]) if f != n - f else np.log(fsp[f])
+                null_tab[base[d] + n + 1 + f] = _libm_log(fsp[f] + fsp[n - f]) if f != n - f else _libm_log(fsp[f])
         cls = np.where(snps["folded"] != 0,
                        base[snps["depth_p"]] + depths[snps["depth_p"]] + 1 + snps["obs_freq"],
                        base[snps["depth_p"]] + snps["obs_freq"]).astype(np.int32)

@@ -84,6 +84,8 @@ def test_c4_full_size_permuted_entries_vs_oracle(api, c4):
         o.L.fo_rng_set_perm(C.addressof(g), t)
         perm, blocks, _ = o.block_permute(g, max_blocks=1 << 20)
         got_cls, got_blocks = sc.block_permute(t, rng=api.RNG_PHILOX, seed=77, max_blocks=1 << 20)
+        blocks = blocks.copy()
+        blocks[:, 2] = np.minimum(blocks[:, 2] - blocks[:, 1], len(perm) - blocks[:, 0])     # (i, j, k) -> (i, j, len)
         assert np.array_equal(got_blocks, blocks) and np.array_equal(got_cls, perm)
         pick = np.concatenate([_spread_cells(np.stack([obs["chr"]]), 1)[:6], rng.choice(len(obs), 6, replace=False)]).astype(int)
         flat_t = dict(flat)

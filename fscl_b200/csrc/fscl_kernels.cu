@@ -569,16 +569,56 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
                   const double *__restrict__ tnull_all, const int *__restrict__ trun_all,
                   const int *__restrict__ tnrun_all, const int *__restrict__ icls_all, size_t icls_stride,
                   int flags, unsigned long long *term_counter, double *__restrict__ clr_matrix,
-                  const int *__restrict__ n_tasks_dev) {
-  // pipelined permutation rounds size the grid from a stale (larger) active count; the true task
+                  const int *__restrict__ n_tasks_dev, int n_tasks_max, int *__restrict__ queue, int n_ranges) {
+  // pipelined permutation rounds size the launch from a stale (larger) active count; the true task
   // count of the round lives on the device (taskgen_kernel)
-  if (n_tasks_dev && (int)blockIdx.x >= *n_tasks_dev) return;
+  const int n_total = n_tasks_dev ? min(*n_tasks_dev, n_tasks_max) : n_tasks_max;
   __shared__ PtS A, B, M;
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
   __shared__ int s_row, s_next, s_redo;
   __shared__ PhaseScratch W;
-  const Task t = tasks[blockIdx.x];
+  __shared__ int s_ti;
+  // Persistent mode (queue != NULL): one CTA per SM slot loops over tasks.  The task list is cut into n_ranges
+  // contiguous ranges, range r served first by the CTAs resident on SM r: tasks are ordered by (permutation slot,
+  // cell), so the CTAs of one SM work on NEIGHBOURING cells at the same time and one after the other -- their near
+  // fields (records, log-table entries, spline rows) overlap and stay in that SM's L1.  A CTA whose range is
+  // exhausted takes tasks from the following ranges.  Results do not depend on who computes a task.
+  unsigned long long nterms = 0;
+#ifdef FSCL_TIMING
+  if (threadIdx.x == 0) for (int q = 0; q < 16; q++) W.tacc[q] = 0;
+#endif
+#ifdef FSCL_HIST
+  for (int q = threadIdx.x; q < 128; q += kScanThreads) (&W.hist[0][0][0])[q] = 0ull;
+#endif
+  int my_range = 0, steal = 0;
+  if (queue) {
+    unsigned smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    my_range = (int)(smid % (unsigned)n_ranges);
+  }
+  for (int iter = 0;; iter++) {
+  int ti;
+  if (!queue) {
+    ti = (iter == 0 && (int)blockIdx.x < n_total) ? (int)blockIdx.x : -1;
+  } else {
+    if (threadIdx.x == 0) {
+      int got = -1;
+      const int per = (n_total + n_ranges - 1) / n_ranges;
+      for (; steal < n_ranges; steal++) {
+        const int r = (my_range + steal) % n_ranges;
+        const int lo = r * per, len = min(per, n_total - lo);
+        if (len <= 0) continue;
+        const int i = atomicAdd(queue + r, 1);
+        if (i < len) { got = lo + i; break; }
+      }
+      s_ti = got;
+    }
+    __syncthreads();
+    ti = s_ti;
+  }
+  if (ti < 0) break;
+  const Task t = tasks[ti];
   const int *__restrict__ tkey = tkey_all + (size_t)t.slot * P.n_pad;
   const int *__restrict__ tpos = tpos_all + (size_t)t.slot * P.n_pad;
   const double *__restrict__ tnull = tnull_all + (size_t)t.slot * (P.n_pad / kTile);
@@ -586,15 +626,10 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   const int *__restrict__ tnrun = tnrun_all + (size_t)t.slot * (P.n_pad / kTile);
   const int *__restrict__ icls = icls_all + (size_t)t.slot * icls_stride;
   const bool prune = !(flags & kFlagNoPrune);
-  unsigned long long nterms = 0;
-
 #ifdef FSCL_TIMING
-  if (threadIdx.x == 0) { for (int q = 0; q < 16; q++) W.tacc[q] = 0; W.tlast = clock64(); }
+  if (threadIdx.x == 0) W.tlast = clock64();
 #endif
   if (threadIdx.x == 0) W.bmF = 0;
-#ifdef FSCL_HIST
-  for (int q = threadIdx.x; q < 128; q += kScanThreads) (&W.hist[0][0][0])[q] = 0ull;
-#endif
   if (prune) {
     // bounds of the far tiles, once for every position the search of this cell can visit
     if (threadIdx.x < 32) {
@@ -666,9 +701,11 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     o.chr = t.chr; o.nearest = A.nearest; o.sweep_pos = A.sweep_pos;
     o.n_snps = A.wend - A.wstart + 1; o.wstart = A.wstart; o.wend = A.wend;
     o.lalpha = A.lalpha; o.clr = A.clr; o.null_logl = A.nsum;
-    if (out) out[blockIdx.x] = o;
+    if (out) out[ti] = o;
     if (clr_matrix) clr_matrix[t.dst] = A.clr;
   }
+  __syncthreads();            // the shared state is re-used by the next task
+  }   // task loop
 #ifdef FSCL_TIMING
   if (threadIdx.x == 0)
     for (int q = 0; q < 14; q++) atomicAdd(term_counter + 2 + q, (unsigned long long)W.tacc[q]);
@@ -687,12 +724,19 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
 }
 
 void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
-                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s, const int *n_tasks_dev) {
+                 unsigned long long *term_counter, double *clr_matrix, cudaStream_t s, const int *n_tasks_dev,
+                 int *queue, int n_sm) {
   if (n_tasks <= 0) return;
+  int grid = n_tasks, n_ranges = 1;
+  if (queue && n_sm > 0 && n_tasks > n_sm * kScanMinBlocks) {
+    // persistent: one CTA per resident slot; the queue counters are zeroed in stream order
+    grid = n_sm * kScanMinBlocks; n_ranges = n_sm;
+    cudaMemsetAsync(queue, 0, sizeof(int) * (size_t)n_ranges, s);
+  } else queue = nullptr;
   if (flags & kFlagCount)
-    scan_cells_kernel<true><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev);
+    scan_cells_kernel<true><<<grid, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev, n_tasks, queue, n_ranges);
   else
-    scan_cells_kernel<false><<<n_tasks, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev);
+    scan_cells_kernel<false><<<grid, kScanThreads, 0, s>>>(P, tasks, out, ts.key, ts.pos, ts.tnull, ts.run, ts.nrun, ts.cls, ts.cls_stride, flags, term_counter, clr_matrix, n_tasks_dev, n_tasks, queue, n_ranges);
 }
 
 // ---------------------------------------------------------------------------

@@ -45,49 +45,77 @@ __device__ double d_ascprob(const double *lf, int k, int d, int min_obs, int n) 
   return 1.0 - no_asc;
 }
 
-// asc-bias.c:27-52 (sequential sums: one thread)
-__global__ void adjust_background_kernel(const double *lf, const double *bsf, int n, int asc_depth, int min_obs,
-                                         double *asc, double *adj) {
-  if (threadIdx.x || blockIdx.x) return;
-  asc[0] = asc[n] = 0.;
-  double asc_sum = 0., adj_sum = 0.;
-  for (int i = 1; i < n; i++) { asc[i] = d_ascprob(lf, i, asc_depth, min_obs, n); asc_sum += asc[i]; }
-  for (int i = 1; i < n; i++) asc[i] /= asc_sum;
-  adj[0] = adj[n] = 0.;
-  for (int i = 1; i < n; i++) { adj[i] = bsf[i] / asc[i]; adj_sum += adj[i]; }
-  for (int i = 1; i < n; i++) adj[i] /= adj_sum;
+// Everything below runs for ALL sample depths in one launch per stage (blockIdx.z / .y = depth); the
+// per-depth inputs and outputs sit in packed arrays addressed through a descriptor table.
+struct DepthDesc {
+  int n;                 // sample depth
+  int spline_base;       // first class (= spline) of this depth; y / coef offsets follow from it
+  long long off_vec;     // offset of this depth's (n + 1)-vectors: fsp, bg, asc
+  long long off_sq;      // offset of its (n + 1) x (n + 1) matrices: pjh, pbk
+};
+
+// asc-bias.c:27-52: the ascertainment probabilities in parallel, the two normalisations by one thread in the
+// reference's summation order
+__global__ void __launch_bounds__(128) adjust_background_kernel(const double *lf, const DepthDesc *dd,
+                                                                const double *fsp_all, int asc_depth, int min_obs,
+                                                                double *asc_all, double *bg_all) {
+  const DepthDesc D = dd[blockIdx.x];
+  const int n = D.n;
+  const double *bsf = fsp_all + D.off_vec;
+  double *asc = asc_all + D.off_vec, *adj = bg_all + D.off_vec;
+  for (int i = 1 + threadIdx.x; i < n; i += blockDim.x) asc[i] = d_ascprob(lf, i, asc_depth, min_obs, n);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asc[0] = asc[n] = 0.;
+    double asc_sum = 0., adj_sum = 0.;
+    for (int i = 1; i < n; i++) asc_sum += asc[i];
+    for (int i = 1; i < n; i++) asc[i] /= asc_sum;
+    adj[0] = adj[n] = 0.;
+    for (int i = 1; i < n; i++) { adj[i] = bsf[i] / asc[i]; adj_sum += adj[i]; }
+    for (int i = 1; i < n; i++) adj[i] /= adj_sum;
+  }
 }
 
 // sm-spline.c:337-351; only h >= j is ever read (:396-401)
-__global__ void pjh_kernel(const double *lf, const double *fsp, int n, double *pjh) {
+__global__ void pjh_kernel(const double *lf, const DepthDesc *dd, const double *bg_all, double *pjh_all) {
+  const DepthDesc D = dd[blockIdx.z];
+  const int n = D.n;
   const int h = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-  if (h > n || h < j) return;
+  if (j > n || h > n || h < j) return;
+  const double *fsp = bg_all + D.off_vec;
   double s = 0.;
   for (int i = j; i <= n; i++)
     s += fsp[i] * exp(d_lchoose(lf, i, j) + d_lchoose(lf, n - i, h - j) - d_lchoose(lf, n, h));
-  pjh[(size_t)j * (n + 1) + h] = s;
+  pjh_all[D.off_sq + (size_t)j * (n + 1) + h] = s;
 }
 
 // sm-spline.c:354-403
-__global__ void pbk_kernel(const double *pjh, int n, double *pbk) {
+__global__ void pbk_kernel(const DepthDesc *dd, const double *pjh_all, double *pbk_all) {
+  const DepthDesc D = dd[blockIdx.z];
+  const int n = D.n;
   const int k = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (k >= n) return;
+  if (k >= n || b > n) return;
   const size_t W = n + 1;
+  const double *pjh = pjh_all + D.off_sq;
   double s = 0.;
   const int q = b - (n - k) + 1;
   if (q > 0) s += pjh[q * W + k + 1] * (q / (double)(k + 1));
   if (b < k + 1) s += pjh[b * W + k + 1] * ((k + 1 - b) / (double)(k + 1));
-  pbk[b * W + k] = s;
+  pbk_all[D.off_sq + b * W + k] = s;
 }
 
-// sm-spline.c:423-462: one block per knot
-__global__ void knots_kernel(const double *lf, const double *fsp, const double *pbk, int n, int spline_pts,
-                             int asc_depth, int asc_min_freq, int ascbias_background_only, int include_invariant,
-                             double *y /* [n+1][P] */, double *fy /* [n/2+1][P] */) {
+// sm-spline.c:423-462: one block per (knot, depth)
+__global__ void knots_kernel(const double *lf, const DepthDesc *dd, const double *bg_all, const double *pbk_all,
+                             int spline_pts, int asc_depth, int asc_min_freq, int ascbias_background_only,
+                             int include_invariant, double *y_all /* [spline][P] */) {
   extern __shared__ double sh[];
+  const DepthDesc D = dd[blockIdx.y];
+  const int n = D.n;
   double *pk = sh, *p = sh + (n + 1), *ap = sh + 2 * (n + 1);
   const int i = blockIdx.x, P = spline_pts + 1;
   const size_t W = n + 1;
+  const double *fsp = bg_all + D.off_vec, *pbk = pbk_all + D.off_sq;
+  double *y = y_all + (size_t)D.spline_base * P, *fy = y + (size_t)(n + 1) * P;
   const double log_ad_step = (4.0 - (-20.0)) / (spline_pts + 1.);
   const double log_ad = -20.0 + i * log_ad_step;
   const double ad = exp(log_ad);
@@ -123,27 +151,34 @@ __global__ void knots_kernel(const double *lf, const double *fsp, const double *
   }
 }
 
-// estimate_spline + solve_linear_system, one thread per spline.  The 4n x 4n system is kept as a
-// window of 16 columns around the diagonal (all the reference ever touches: columns i..i+7 of rows
-// i..i+7), element (r, c) at m[r*16 + (c - r + 8)].
+// estimate_spline + solve_linear_system (sm-spline.c:63-220), ONE WARP PER SPLINE.  The 4n x 4n system is
+// kept as a window of 16 columns around the diagonal (all the reference ever touches: columns i..i+7 of rows
+// i..i+7), element (r, c) at m[r*16 + (c - r + 8)].  One elimination step of the reference -- normalise the
+// pivot row, then subtract it from the 7 rows below over 8 columns -- is 8 + 56 + 7 independent
+// element updates: the lanes of the warp take them in parallel, every element with the reference's own
+// expression (a / f, a - b * f: one division or one fused multiply-subtract, as gcc emits them), so the
+// result equals the sequential elimination bit for bit for equal inputs.  Only the steps are sequential.
 constexpr int kBW = 16;
 __device__ __forceinline__ double &M(double *m, int r, int c) { return m[(size_t)r * kBW + (c - r + 8)]; }
 
-__global__ void spline_kernel(const double *yall, int n_splines, int n /* spline_pts */, double *scratch,
-                              double *coef_out /* [n_splines][n][4] */, int *flags) {
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) spline_kernel(const double *yall, int n_splines, int n /* spline_pts */,
+                                                     double *scratch, double *coef_out /* [n_splines][n][4] */,
+                                                     int *flags) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s >= n_splines) return;
+  const unsigned full = 0xFFFFFFFFu;
   const int N = 4 * n, P = n + 1;
   const double *y = yall + (size_t)s * P;
-  double *m = scratch + (size_t)s * ((size_t)(N + 8) * kBW + 2 * (size_t)(N + 8));
+  const size_t per = (size_t)(N + 8) * kBW + 2 * (size_t)(N + 8);
+  double *m = scratch + (size_t)s * per;
   double *v = m + (size_t)(N + 8) * kBW, *b = v + (N + 8);
-  for (size_t q = 0; q < (size_t)(N + 8) * kBW + 2 * (size_t)(N + 8); q++) m[q] = 0.;
+  for (size_t q = lane; q < per; q += 32) m[q] = 0.;
+  __syncwarp();
   const double step = (4.0 - (-20.0)) / (n + 1.);
   auto X = [&](int k) { return -20.0 + k * step; };
-  M(m, 0, 0) = 6 * X(0);
-  M(m, 0, 1) = 2;
-  int i, j, k;
-  for (i = 1, j = 0, k = 0; k < n - 1; i += 4, j += 4, k++) {
+  if (lane == 0) { M(m, 0, 0) = 6 * X(0); M(m, 0, 1) = 2; }
+  for (int k = lane; k < n - 1; k += 32) {                 // sm-spline.c:137-180: four rows per interior knot
+    const int i = 1 + 4 * k, j = 4 * k;
     const double xk = X(k), x1 = X(k + 1);
     M(m, i, j) = xk * xk * xk; M(m, i, j + 1) = xk * xk; M(m, i, j + 2) = xk; M(m, i, j + 3) = 1.;
     v[i] = y[k];
@@ -156,7 +191,8 @@ __global__ void spline_kernel(const double *yall, int n_splines, int n /* spline
     M(m, i + 3, j + 4) = -6 * x1; M(m, i + 3, j + 5) = -2; M(m, i + 3, j + 6) = 0; M(m, i + 3, j + 7) = 0;
     v[i + 3] = 0;
   }
-  {
+  if (lane == 0) {                                          // the last interval, sm-spline.c:182-197
+    const int k = n - 1, i = 1 + 4 * k, j = 4 * k;
     const double xk = X(k), xn = X(n);
     M(m, i, j) = xk * xk * xk; M(m, i, j + 1) = xk * xk; M(m, i, j + 2) = xk; M(m, i, j + 3) = 1;
     v[i] = y[k];
@@ -165,34 +201,61 @@ __global__ void spline_kernel(const double *yall, int n_splines, int n /* spline
     M(m, i + 2, j) = 6 * xn; M(m, i + 2, j + 1) = 2; M(m, i + 2, j + 2) = 0; M(m, i + 2, j + 3) = 0;
     v[i + 2] = 0;
   }
+  __syncwarp();
   int flag = 0;
-  for (i = 0; i < N; i++) {
-    if (fabs(M(m, i, i)) < 1e-20) {          // sm-spline.c:67-88 inside the band (rows beyond hold zeros)
-      int mx = i;
-      for (j = i + 1; j < N && j < i + 8; j++)
-        if (fabs(M(m, j, i)) > 0 && (mx == i || fabs(fabs(M(m, j, i)) - 1) < fabs(fabs(M(m, mx, i)) - 1))) mx = j;
-      if (mx == i) { flag |= 1; break; }
-      for (k = i; k < i + 8 && k < N; k++) if (k - mx < 8 && k - mx >= -8) M(m, i, k) += M(m, mx, k);
-      v[i] += v[mx];
-      flag |= 2;
+  bool dead = false;
+  for (int i = 0; i < N && !dead; i++) {
+    double piv = M(m, i, i);                               // every lane reads the pivot
+    if (fabs(piv) < 1e-20) {                               // sm-spline.c:67-88 inside the band (rows beyond hold zeros): rare, serial
+      if (lane == 0) {
+        int mx = i;
+        for (int j = i + 1; j < N && j < i + 8; j++)
+          if (fabs(M(m, j, i)) > 0 && (mx == i || fabs(fabs(M(m, j, i)) - 1) < fabs(fabs(M(m, mx, i)) - 1))) mx = j;
+        if (mx == i) flag |= 1;
+        else {
+          for (int k = i; k < i + 8 && k < N; k++) if (k - mx < 8 && k - mx >= -8) M(m, i, k) += M(m, mx, k);
+          v[i] += v[mx];
+          flag |= 2;
+        }
+      }
+      __syncwarp();
+      flag = __shfl_sync(full, flag, 0);
+      if (flag & 1) { dead = true; break; }
+      piv = M(m, i, i);
     }
-    double f = M(m, i, i);
-    for (k = i; k < i + 8 && k < N; k++) M(m, i, k) /= f;
-    v[i] /= f;
-    for (j = i + 1; j < i + 8 && j < N; j++) {
-      f = M(m, j, i);
-      for (k = i; k < i + 8 && k < N; k++) M(m, j, k) = M(m, j, k) - M(m, i, k) * f;
-      v[j] = v[j] - v[i] * f;
+    // lanes 0..7: column i + lane of the pivot row; lanes 0..6 also hold the multiplier of row i + 1 + lane
+    const int c8 = lane & 7;
+    double prow = 0., fcol = 0.;
+    if (lane < 8 && i + lane < N) prow = M(m, i, i + lane) / piv;
+    if (lane < 7 && i + 1 + lane < N) fcol = M(m, i + 1 + lane, i);
+    if (lane < 8 && i + lane < N) M(m, i, i + lane) = prow;
+    double vi = 0.;
+    if (lane == 0) { vi = v[i] / piv; v[i] = vi; }
+    vi = __shfl_sync(full, vi, 0);
+#pragma unroll
+    for (int pass = 0; pass < 2; pass++) {
+      const int pr = lane + 32 * pass, r = pr >> 3;        // pair (row offset r + 1, column offset c8), 56 pairs
+      const double f = __shfl_sync(full, fcol, r < 7 ? r : 0);
+      const double pc = __shfl_sync(full, prow, c8);
+      if (r < 7 && i + 1 + r < N && i + c8 < N) {
+        double &e = M(m, i + 1 + r, i + c8);
+        e = e - pc * f;
+      }
+    }
+    if (lane < 7 && i + 1 + lane < N) v[i + 1 + lane] = v[i + 1 + lane] - vi * fcol;
+    __syncwarp();
+  }
+  if (lane == 0 && !dead) {                                // back substitution: a dependent chain, sm-spline.c:105-116
+    for (int i = N - 1; i >= 0; i--) {
+      if (fabs(M(m, i, i)) < 1e-10) { b[i] = 0; flag |= 4; continue; }
+      b[i] = v[i];
+      for (int k = i + 1; k < i + 8 && k < N; k++) b[i] -= M(m, i, k) * b[k];
     }
   }
-  for (i = N - 1; i >= 0; i--) {
-    if (fabs(M(m, i, i)) < 1e-10) { b[i] = 0; flag |= 4; continue; }
-    b[i] = v[i];
-    for (k = i + 1; k < i + 8 && k < N; k++) b[i] -= M(m, i, k) * b[k];
-  }
+  __syncwarp();
   double *out = coef_out + (size_t)s * N;
-  for (i = 0; i < N; i++) out[i] = b[i];
-  if (flag) atomicOr(flags, flag);
+  if (!dead) for (int i = lane; i < N; i += 32) out[i] = b[i];
+  if (lane == 0 && flag) atomicOr(flags, flag);
 }
 
 }  // namespace
@@ -206,8 +269,16 @@ static int tfail(int code, const std::string &m) { return fscl_set_error(code, m
     if (e_ != cudaSuccess) return tfail(FSCL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+namespace {
+struct DeviceBlock {               // one allocation for the whole build, released on every path
+  char *p = nullptr;
+  ~DeviceBlock() { if (p) cudaFree(p); }
+};
+}  // namespace
+
 // compute_sweep_model_tables (sm-spline.c:486-523) + the class-indexed null model
 // (scan-chromosome.c:23-37) for all depths; outputs use the class layout of fscl_problem_t.
+// One device allocation, five launches (every stage covers all depths), one copy back.
 extern "C" int fscl_build_tables(int device, int n_depths, const int32_t *depths, const double *const *fsp,
                                  int spline_pts, int asc_depth, int asc_min_freq, int ascbias_background_only,
                                  int include_invariant, double *coef_out, double *null_out, int32_t *flags_out) {
@@ -217,60 +288,73 @@ extern "C" int fscl_build_tables(int device, int n_depths, const int32_t *depths
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return tfail(FSCL_ERR_NODEVICE, "no CUDA device: fscl_b200 has no CPU path"); }
   TCK(cudaSetDevice(device));
   int max_n = 0;
-  for (int d = 0; d < n_depths; d++) max_n = std::max(max_n, depths[d]);
+  for (int d = 0; d < n_depths; d++) {
+    if (depths[d] < 2) return tfail(FSCL_ERR_ARG, "sample depth below 2");
+    max_n = std::max(max_n, depths[d]);
+  }
   const int lf_n = std::max(max_n, asc_depth) + 2;
   std::vector<double> lf(lf_n + 1, 0.0);                 // log_fact's running sum, sm-spline.c:30-36
   for (int i = 1; i <= lf_n; i++) lf[i] = lf[i - 1] + std::log((double)i);
   const int K = spline_pts, P = K + 1, N = 4 * K;
-  const size_t W = (size_t)max_n + 1;
-  const int max_splines = (max_n + 1) + (max_n / 2 + 1);
+  std::vector<DepthDesc> desc(n_depths);
+  long long vec = 0, sq = 0;
+  int n_splines = 0;
+  for (int d = 0; d < n_depths; d++) {
+    const int n = depths[d];
+    desc[d] = DepthDesc{n, n_splines, vec, sq};
+    vec += n + 1; sq += (long long)(n + 1) * (n + 1);
+    n_splines += (n + 1) + (n / 2 + 1);
+  }
+  std::vector<double> fsp_all((size_t)vec);
+  for (int d = 0; d < n_depths; d++) memcpy(fsp_all.data() + desc[d].off_vec, fsp[d], sizeof(double) * (size_t)(depths[d] + 1));
   const size_t per_spline = (size_t)(N + 8) * kBW + 2 * (size_t)(N + 8);
-  double *d_lf = nullptr, *d_fsp = nullptr, *d_bg = nullptr, *d_asc = nullptr, *d_pjh = nullptr, *d_pbk = nullptr,
-         *d_y = nullptr, *d_scratch = nullptr, *d_coef = nullptr;
-  int *d_flags = nullptr;
-  TCK(cudaMalloc(&d_lf, sizeof(double) * lf.size()));
-  TCK(cudaMalloc(&d_fsp, sizeof(double) * W));
-  TCK(cudaMalloc(&d_bg, sizeof(double) * W));
-  TCK(cudaMalloc(&d_asc, sizeof(double) * W));
-  TCK(cudaMalloc(&d_pjh, sizeof(double) * W * W));
-  TCK(cudaMalloc(&d_pbk, sizeof(double) * W * W));
-  TCK(cudaMalloc(&d_y, sizeof(double) * (size_t)max_splines * P));
-  TCK(cudaMalloc(&d_scratch, sizeof(double) * (size_t)max_splines * per_spline));
-  TCK(cudaMalloc(&d_coef, sizeof(double) * (size_t)max_splines * N));
-  TCK(cudaMalloc(&d_flags, sizeof(int)));
-  TCK(cudaMemset(d_flags, 0, sizeof(int)));
-  TCK(cudaMemcpy(d_lf, lf.data(), sizeof(double) * lf.size(), cudaMemcpyHostToDevice));
+  // carve one block: descriptors | lf | fsp | bg | asc | pjh | pbk | y | coef | scratch | flags
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  const size_t o_desc = carve(sizeof(DepthDesc) * (size_t)n_depths), o_lf = carve(sizeof(double) * lf.size());
+  const size_t o_fsp = carve(sizeof(double) * (size_t)vec), o_bg = carve(sizeof(double) * (size_t)vec);
+  const size_t o_asc = carve(sizeof(double) * (size_t)vec);
+  const size_t o_pjh = carve(sizeof(double) * (size_t)sq), o_pbk = carve(sizeof(double) * (size_t)sq);
+  const size_t o_y = carve(sizeof(double) * (size_t)n_splines * P), o_coef = carve(sizeof(double) * (size_t)n_splines * N);
+  const size_t o_scr = carve(sizeof(double) * (size_t)n_splines * per_spline), o_flags = carve(sizeof(int));
+  DeviceBlock blk;
+  TCK(cudaMalloc((void **)&blk.p, off));
+  DepthDesc *d_desc = (DepthDesc *)(blk.p + o_desc);
+  double *d_lf = (double *)(blk.p + o_lf), *d_fsp = (double *)(blk.p + o_fsp), *d_bg = (double *)(blk.p + o_bg);
+  double *d_asc = (double *)(blk.p + o_asc), *d_pjh = (double *)(blk.p + o_pjh), *d_pbk = (double *)(blk.p + o_pbk);
+  double *d_y = (double *)(blk.p + o_y), *d_coef = (double *)(blk.p + o_coef), *d_scratch = (double *)(blk.p + o_scr);
+  int *d_flags = (int *)(blk.p + o_flags);
+  TCK(cudaMemsetAsync(d_flags, 0, sizeof(int)));
+  TCK(cudaMemsetAsync(d_pjh, 0, sizeof(double) * (size_t)sq));
+  TCK(cudaMemcpyAsync(d_desc, desc.data(), sizeof(DepthDesc) * (size_t)n_depths, cudaMemcpyHostToDevice));
+  TCK(cudaMemcpyAsync(d_lf, lf.data(), sizeof(double) * lf.size(), cudaMemcpyHostToDevice));
+  TCK(cudaMemcpyAsync(d_fsp, fsp_all.data(), sizeof(double) * (size_t)vec, cudaMemcpyHostToDevice));
+  const double *bg = d_fsp;
+  if (asc_depth > 0) {                                    // sm-spline.c:500-505
+    adjust_background_kernel<<<n_depths, 128>>>(d_lf, d_desc, d_fsp, asc_depth, asc_min_freq, d_asc, d_bg);
+    bg = d_bg;
+  }
+  const unsigned gx = (unsigned)(max_n + 1 + 127) / 128;
+  pjh_kernel<<<dim3(gx, max_n + 1, n_depths), 128>>>(d_lf, d_desc, bg, d_pjh);
+  pbk_kernel<<<dim3(gx, max_n + 1, n_depths), 128>>>(d_desc, d_pjh, d_pbk);
+  knots_kernel<<<dim3(P, n_depths), 128, sizeof(double) * 3 * (max_n + 1)>>>(d_lf, d_desc, bg, d_pbk, K, asc_depth, asc_min_freq,
+                                                                            ascbias_background_only, include_invariant, d_y);
+  spline_kernel<<<(n_splines + 3) / 4, 128>>>(d_y, n_splines, K, d_scratch, d_coef, d_flags);
+  TCK(cudaGetLastError());
+  TCK(cudaMemcpy(coef_out, d_coef, sizeof(double) * (size_t)n_splines * N, cudaMemcpyDeviceToHost));
+  int flags = 0;
+  TCK(cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost));
+  // null model per class with the host's libm, exactly as compute_snp_null_model
   size_t base = 0;
   for (int d = 0; d < n_depths; d++) {
     const int n = depths[d];
-    const int ns = (n + 1) + (n / 2 + 1);
-    TCK(cudaMemcpy(d_fsp, fsp[d], sizeof(double) * (n + 1), cudaMemcpyHostToDevice));
-    const double *bg = d_fsp;
-    if (asc_depth > 0) {                                  // sm-spline.c:500-505
-      adjust_background_kernel<<<1, 1>>>(d_lf, d_fsp, n, asc_depth, asc_min_freq, d_asc, d_bg);
-      bg = d_bg;
-    }
-    TCK(cudaMemset(d_pjh, 0, sizeof(double) * W * W));
-    pjh_kernel<<<dim3((n + 1 + 127) / 128, n + 1), 128>>>(d_lf, bg, n, d_pjh);
-    pbk_kernel<<<dim3((n + 127) / 128, n + 1), 128>>>(d_pjh, n, d_pbk);
-    knots_kernel<<<P, 128, sizeof(double) * 3 * (n + 1)>>>(d_lf, bg, d_pbk, n, K, asc_depth, asc_min_freq,
-                                                            ascbias_background_only, include_invariant, d_y,
-                                                            d_y + (size_t)(n + 1) * P);
-    spline_kernel<<<(ns + 31) / 32, 32>>>(d_y, ns, K, d_scratch, d_coef, d_flags);
-    TCK(cudaGetLastError());
-    TCK(cudaMemcpy(coef_out + base * N, d_coef, sizeof(double) * (size_t)ns * N, cudaMemcpyDeviceToHost));
-    // null model per class with the host's libm, exactly as compute_snp_null_model
     const double *f = fsp[d];
     for (int q = 0; q <= n; q++) null_out[base + q] = std::log(f[q]);
     for (int q = 0; q <= n / 2; q++)
       null_out[base + n + 1 + q] = (q != n - q) ? std::log(f[q] + f[n - q]) : std::log(f[q]);
-    base += ns;
+    base += (size_t)(n + 1) + (n / 2 + 1);
   }
-  int flags = 0;
-  TCK(cudaMemcpy(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost));
   if (flags_out) *flags_out = flags;
-  cudaFree(d_lf); cudaFree(d_fsp); cudaFree(d_bg); cudaFree(d_asc); cudaFree(d_pjh); cudaFree(d_pbk);
-  cudaFree(d_y); cudaFree(d_scratch); cudaFree(d_coef); cudaFree(d_flags);
   if (flags & 1) return tfail(FSCL_ERR_ARG, "ill conditioned spline system (sm-spline.c:78)");
   return FSCL_OK;
 }

@@ -1056,9 +1056,10 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
   const int lim = slot_limit(c);
   // at least 4 permutations per rank and round: the swaps of ONE permutation are a single CTA, so a round
   // of one would leave most of the GPU idle behind it
+  // ... and enough permutations that EVERY rank launches about 16384 searches once few cells are left
   int R = o.round_perms > 0 ? o.round_perms
                             : (int)std::min<size_t>((size_t)kMaxRoundPerRank * S.stride,
-                                                    std::max<size_t>(4 * (size_t)S.stride, (16384 + na - 1) / na));
+                                                    std::max<size_t>(4, (16384 + na - 1) / na) * (size_t)S.stride);
   R = (R + S.stride - 1) / S.stride * S.stride;
   R = std::min(R, lim * S.stride);
   R = std::min(R, o.n_permute - S.t_next + 1);
@@ -1908,11 +1909,12 @@ extern "C" int fscl_bench_scan(void *ctx, int G, int n_perm_slots, int count_ter
     c->stats.n_blocks += (int64_t)blocks.size();
   }
   c->h_tasks.resize((size_t)ns * cells.size());
+  const bool cell_major = getenv("FSCL_B200_CELL_MAJOR") != nullptr;      // experiment: task order (cell, slot) instead of (slot, cell)
   for (int q = 0; q < ns; q++)
     for (size_t a = 0; a < cells.size(); a++) {
       Task t = cells[a]; t.slot = q;
       if (n_perm_slots > 0) { t.start_pos = t.start_pos - (t.start_pos % G); t.end_pos = t.start_pos + G; }
-      c->h_tasks[(size_t)q * cells.size() + a] = t;
+      c->h_tasks[cell_major ? a * (size_t)ns + q : (size_t)q * cells.size() + a] = t;
     }
   if (count_terms) CK(cudaMemsetAsync(c->d_terms, 0, sizeof(unsigned long long), c->stream));
   int rc = run_tasks(c, n_perm_slots > 0, count_terms ? kFlagCount : 0, false);

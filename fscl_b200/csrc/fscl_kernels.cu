@@ -10,10 +10,13 @@ void upload_alpha_tables(const AlphaTables &t) { cudaMemcpyToSymbol(c_alpha, &t,
 
 // ---------------------------------------------------------------------------
 // logt, sm-search.c:40-46 (D2 constant kept).  d >= 0.
+// one entry of the 64 Ki-entry log table (init_log_table sm-search.c:14-26).  Computing it with the device's log()
+// instead (plus an ulp-correction table to stay bit-exact) was measured: 30 % slower, the lookup is not the limiter.
+__device__ __forceinline__ double lut_entry(const double *__restrict__ T, int i) { return __ldg(T + i); }
 __device__ __forceinline__ double dev_logt(const double *__restrict__ T, int d) {
   int sh = d > 0xFFFFFF ? 16 : (d > 0xFFFF ? 8 : 0);
   double c = d > 0xFFFFFF ? 11.783502069519070 : (d > 0xFFFF ? 5.545177444479562 : 0.0);
-  double t = __ldg(T + (d >> sh));
+  double t = lut_entry(T, d >> sh);
   return sh ? c + t : t;
 }
 
@@ -77,9 +80,6 @@ __device__ __forceinline__ int ld_stream(const int *p) {
   asm("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
 }
-
-// mid-range log-table entries (d >> 8) are touched about once per tile pass
-__device__ __forceinline__ double ld_lut_mid(const double *p) { return __ldg(p); }
 
 // 32-byte coefficient row in one 256-bit load (LDG.E.256)
 __device__ __forceinline__ void ld_row(const double *p, double &c0, double &c1, double &c2, double &c3) {
@@ -423,10 +423,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       }
       if (lut == 2) {
 #pragma unroll
-        for (int u = 0; u < kB; u++) x0[u] = 11.783502069519070 + __ldg(T + (d[u] >> 16));
+        for (int u = 0; u < kB; u++) x0[u] = 11.783502069519070 + lut_entry(T, d[u] >> 16);
       } else if (lut == 1) {
 #pragma unroll
-        for (int u = 0; u < kB; u++) x0[u] = 5.545177444479562 + ld_lut_mid(T + (d[u] >> 8));
+        for (int u = 0; u < kB; u++) x0[u] = 5.545177444479562 + lut_entry(T, d[u] >> 8);
       } else {
 #pragma unroll
         for (int u = 0; u < kB; u++) x0[u] = dev_logt(T, d[u]);
@@ -727,6 +727,8 @@ void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &
                  unsigned long long *term_counter, double *clr_matrix, cudaStream_t s, const int *n_tasks_dev,
                  int *queue, int n_sm) {
   if (n_tasks <= 0) return;
+  // (cudaSharedmemCarveoutMaxL1 was tried: the driver then sizes the carveout for ONE resident CTA and the
+  //  kernel loses a third of its throughput; the default 32 KB configuration keeps two.)
   int grid = n_tasks, n_ranges = 1;
   if (queue && n_sm > 0 && n_tasks > n_sm * kScanMinBlocks) {
     // persistent: one CTA per resident slot; the queue counters are zeroed in stream order

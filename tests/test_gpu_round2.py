@@ -331,3 +331,18 @@ def test_fscl_gpu_two_gpus_equal_one(built, api, tmp_path):
         outs.append((out.read_text(), (tmp_path / f"out{n}.txt-nulldist").read_text(),
                      (tmp_path / f"out{n}.txt-projected").read_text()))
     assert outs[0] == outs[1]
+
+
+def test_persistent_scan_gives_identical_results(api, monkeypatch):
+    """FSCL_B200_PERSISTENT=1: one CTA per SM slot loops over neighbouring cells (per-SM task ranges with stealing);
+    every output byte equals the one-CTA-per-task launch, forward scan and permutation test."""
+    tab, flat, G = problem("mid100")
+    a_sc = api.Scanner(flat)
+    obs_a = a_sc.scan_chromosome(G // 20)                     # 2000 cells: more tasks than resident CTA slots
+    pa, _, ca = a_sc.scan_permute(obs_a[::7], 12, G // 20, save_clr=True, rng=api.RNG_PHILOX, seed=3, prune=0)
+    monkeypatch.setenv("FSCL_B200_PERSISTENT", "1")
+    b_sc = api.Scanner(flat)
+    obs_b = b_sc.scan_chromosome(G // 20)
+    pb, _, cb = b_sc.scan_permute(obs_b[::7], 12, G // 20, save_clr=True, rng=api.RNG_PHILOX, seed=3, prune=0)
+    assert len(obs_a) > 600 and obs_a.tobytes() == obs_b.tobytes()
+    assert pa.tobytes() == pb.tobytes() and np.array_equal(ca, cb)

@@ -6,6 +6,8 @@ cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 slots = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 tab, opt = {2: synth.config2, 4: synth.config4}[cfg]()
 flat = hostref.load_problem(table=tab, device_tables=True)
+if len(sys.argv) > 3:        # the ascertainment kernel of the table build as well
+    api.build_tables(flat["depths"], flat["fsp"], asc_depth=20, asc_min_freq=1)
 sc = api.Scanner(flat)
 G = opt["G"]
 obs = sc.scan_chromosome(G)

@@ -242,7 +242,6 @@ struct Ctx {
   fscl_stats_t stats{};
 };
 
-constexpr int kDebugCounters = 16 + 128;                // see fscl_debug_counters
 constexpr int kPinSlots = 1024;                    // permutations per rank and round the pinned flag area holds
 
 struct SlotRef {
@@ -1868,10 +1867,13 @@ extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !s) return fail(FSCL_ERR_ARG, "bad argument");
   cudaSetDevice(c->device);
-  unsigned long long redo = 0;
+  unsigned long long redo = 0, near[2] = {0, 0};
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(&redo, c->d_terms + 1, sizeof redo, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(near, c->d_terms + kCtrNearAlpha, sizeof near, cudaMemcpyDeviceToHost));
   c->stats.bound_failures = (int32_t)std::min<unsigned long long>(redo, 0x7FFFFFFFull);
+  c->stats.near_ties_alpha = (int64_t)near[0];
+  c->stats.near_ties_position = (int64_t)near[1];
   *s = c->stats;
   return FSCL_OK;
 }
@@ -1880,6 +1882,7 @@ extern "C" int fscl_reset_stats(void *ctx) {
   if (!c) return fail(FSCL_ERR_ARG, "bad argument");
   cudaSetDevice(c->device);
   cudaMemsetAsync(c->d_terms + 1, 0, sizeof(unsigned long long), c->stream);
+  cudaMemsetAsync(c->d_terms + kCtrNearAlpha, 0, 2 * sizeof(unsigned long long), c->stream);
   memset(&c->stats, 0, sizeof c->stats);
   return FSCL_OK;
 }

@@ -117,6 +117,63 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
   }
 }
 
+#ifndef FSCL_TMA
+#define FSCL_TMA 0
+#endif
+// ---- record streams through shared memory (TMA bulk copies + mbarriers): -DFSCL_TMA=1, NOT the default ----
+// The walk reads the class-bucketed records of a tile (tkey, tpos: 2 x 4 KB, contiguous) exactly once per
+// pass; through the LSU that is two streaming loads per 32 records, every sector an L1 miss and a fill
+// wavefront on the pipe that bounds the kernel.  In this variant ONE thread issues two cp.async.bulk (UBLKCP)
+// per tile into a ring; the bytes land in shared memory without touching the LSU pipe and signal the stage's
+// `full` mbarrier (complete_tx); the warps read them with conflict-free LDS.32 and release the stage on its
+// `empty` mbarrier (one arrival per warp); the copy of tile h+2 is in flight while tiles h, h+1 are evaluated.
+// Bit-identical results (the whole GPU suite passes with it) -- and 17 % SLOWER on c2 and c4 (330 vs 401,
+// 13.1 vs 15.7 scans/s; 3 and 4 stages: 325 / 320): the ring's 16-32 KB per CTA come out of the L1 that holds
+// the coefficient rows, and the warps of a CTA advance in step with the slowest one.  Kept as a measured
+// alternative (profiles/r02_optimisation_log.md); the default streams the records with
+// ld.global.nc.L1::no_allocate, one batch ahead, per warp.
+#ifndef FSCL_REC_STAGES
+#define FSCL_REC_STAGES 2
+#endif
+constexpr int kRecStages = FSCL_REC_STAGES;
+struct __align__(128) RecRing {
+  int key[kRecStages][kTile];
+  int pos[kRecStages][kTile];
+  unsigned long long full[kRecStages], empty[kRecStages];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  while (!mbar_test(bar, parity)) { }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// tile `tile` of this pass's list into the stage of ring position g (called by the producer thread only)
+__device__ __forceinline__ void ring_issue(RecRing &ring, unsigned g, const int *__restrict__ tkey, const int *__restrict__ tpos,
+                                           int tile) {
+  const unsigned st = g % kRecStages;
+  mbar_expect_tx(&ring.full[st], 2u * kTile * (unsigned)sizeof(int));
+  bulk_g2s(ring.key[st], tkey + (size_t)tile * kTile, kTile * (unsigned)sizeof(int), &ring.full[st]);
+  bulk_g2s(ring.pos[st], tpos + (size_t)tile * kTile, kTile * (unsigned)sizeof(int), &ring.full[st]);
+}
+
 // One pass over the window for the alpha list in c_alpha row `row`:
 // S[j] = sum over window sites with d <= dmax[j] of spline_cls(logt(d)+la[j]) - null
 // (sm_likelihood sm-search.c:105-150; the walks' "break at first exceed" equals
@@ -145,7 +202,6 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
 struct PhaseScratch {
   int tile[kMaxTilesC];                 // per-tile classification
   int list[kMaxTilesC];                 // tiles that need a per-site walk, in order
-  double tn[kMaxTilesC];                // per-tile null sums (WITHN)
   unsigned kr[kMaxTilesC + 2][kNB];       // dev_cell_bounds: first knot | extra knots << 16 per candidate
   unsigned char jbF[kMaxTilesC + 2];    // cell level: leading candidates of the tile that a bound stands for
   double ubF[kNB];                        // cell level: bound sums per candidate over those tiles
@@ -275,7 +331,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
                                           const int *__restrict__ tpos, const double *__restrict__ tnull,
                                           const int *__restrict__ trun, const int *__restrict__ tnrun,
                                           const int *__restrict__ icls, PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
-                                          PhaseScratch &W, bool use_bound, unsigned long long &nterms) {
+                                          PhaseScratch &W, bool use_bound, unsigned long long &nterms, RecRing &ring,
+                                          unsigned &ring_pos) {
   int *s_tile = W.tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na_all = c_alpha.n[row];
@@ -358,7 +415,6 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       int needed = (WITHN && !ins) || ja > 0;
       int jb = 0;
       if (WITHN) {
-        if (ins) W.tn[t - t0] = __ldg(tnull + t);
         if (bounds_on && t >= W.t0F && t <= W.t1F) {
           jb = min((int)W.jbF[t - W.t0F], jf);       // jf >= jbF by construction (the cell bound used the largest distance)
           if (jb) needed = ja > jb;                   // candidates left for the walk
@@ -387,7 +443,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     // one tile each, the fixed tree of the reduction below does the rest
     if (WITHN)
       for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads)
-        if ((s_tile[t - t0] >> 16) & 1) accn += W.tn[t - t0];
+        if ((s_tile[t - t0] >> 16) & 1) accn += __ldg(tnull + t);
     // A warp owns chunks {warp, warp+8, ...} of every tile and walks them in batches of kB:
     // the kB records of the NEXT batch are fetched while the current one is evaluated,
     // the kB log-distances and the coefficient rows of four alphas are each issued together.
@@ -398,12 +454,22 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     const int n_batches = n_tl * HB;
     const int woff = warp * 32 + lane;
     auto batch_base = [&](int h) { return W.list[h / HB] * kTile + (h % HB) * (kB * kScanWarps * 32) + woff; };
+#if FSCL_TMA
+    // producer = thread 0: the first tiles of this pass (the ring is idle: every warp passed the barrier above
+    // after releasing the stages of the previous pass)
+    const unsigned g0 = ring_pos;                     // ring position of this pass's first tile
+    unsigned issued = 0;                              // tiles of this pass handed to the copy engine (thread 0 only)
+    if (threadIdx.x == 0)
+      for (; issued < (unsigned)min(n_tl, kRecStages); issued++) ring_issue(ring, g0 + issued, tkey, tpos, W.list[issued]);
+    (void)batch_base;
+#else
     int nkey[kB], npos[kB];
     if (n_batches > 0) {
       const int i = batch_base(0);
 #pragma unroll
       for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
     }
+#endif
     int jany = 0, jfull = 0, lut = 0, jskip = 0;
     bool inside = false;
     for (int h = 0; h < n_batches; h++) {
@@ -415,12 +481,48 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       }
       int key[kB], d[kB];
       double x0[kB];
+#if FSCL_TMA
+      {
+        const unsigned g = g0 + (unsigned)(h / HB), st = g % kRecStages;
+        if (h % HB == 0) {
+          // the producer makes sure this tile is on its way before anybody (itself included) waits for it:
+          // its stage was last used by tile g - kRecStages, which every warp has long released
+          if (threadIdx.x == 0)
+            for (; issued <= (unsigned)(h / HB); issued++) {
+              const unsigned gi = g0 + issued;
+              if (gi >= kRecStages) mbar_wait(&ring.empty[gi % kRecStages], ((gi / kRecStages) - 1u) & 1u);
+              ring_issue(ring, gi, tkey, tpos, W.list[issued]);
+            }
+          mbar_wait(&ring.full[st], (g / kRecStages) & 1u);
+        }
+        const int o = (h % HB) * (kB * kScanWarps * 32) + woff;
+#pragma unroll
+        for (int u = 0; u < kB; u++) {
+          key[u] = ring.key[st][o + u * kScanWarps * 32];
+          const int dd = ring.pos[st][o + u * kScanWarps * 32] - sweep;
+          d[u] = dd < 0 ? -dd : dd;
+        }
+        if (h % HB == HB - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ring.empty[st]);      // this warp has its records of the tile in registers
+          // refill whatever stage has been released by all warps (never blocks)
+          if (threadIdx.x == 0)
+            while (issued < (unsigned)n_tl) {
+              const unsigned gi = g0 + issued;
+              if (gi >= kRecStages && !mbar_test(&ring.empty[gi % kRecStages], ((gi / kRecStages) - 1u) & 1u)) break;
+              ring_issue(ring, gi, tkey, tpos, W.list[issued]);
+              issued++;
+            }
+        }
+      }
+#else
 #pragma unroll
       for (int u = 0; u < kB; u++) {
         key[u] = nkey[u];
         const int dd = npos[u] - sweep;
         d[u] = dd < 0 ? -dd : dd;
       }
+#endif
       if (lut == 2) {
 #pragma unroll
         for (int u = 0; u < kB; u++) x0[u] = 11.783502069519070 + lut_entry(T, d[u] >> 16);
@@ -431,11 +533,13 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
         for (int u = 0; u < kB; u++) x0[u] = dev_logt(T, d[u]);
       }
+#if !FSCL_TMA
       if (h + 1 < n_batches) {
         const int i = batch_base(h + 1);
 #pragma unroll
         for (int u = 0; u < kB; u++) { nkey[u] = ld_stream(tkey + i + u * kScanWarps * 32); npos[u] = ld_stream(tpos + i + u * kScanWarps * 32); }
       }
+#endif
       const char *crow[kB];
       int dq[kB];
 #pragma unroll
@@ -516,6 +620,9 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
         }
       }
     }
+#if FSCL_TMA
+    ring_pos = g0 + (unsigned)n_tl;
+#endif
   }
   FSCL_TICK(W, (WITHN ? 4 : 9));
   // fixed-tree reduction: deterministic, independent of launch shape
@@ -578,7 +685,20 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   __shared__ double S[kMaxFine + 1];
   __shared__ int s_row, s_next, s_redo;
   __shared__ PhaseScratch W;
+#if FSCL_TMA
+  __shared__ RecRing ring;
+#else
+  RecRing &ring = *reinterpret_cast<RecRing *>(&W);      // unused placeholder: no shared memory is reserved
+#endif
   __shared__ int s_ti;
+  unsigned ring_pos = 0;                     // tiles that went through the record ring so far (same in every thread)
+#if FSCL_TMA
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < kRecStages; q++) { mbar_init(&ring.full[q], 1); mbar_init(&ring.empty[q], kScanWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+#endif
   // Persistent mode (queue != NULL): one CTA per SM slot loops over tasks.  The task list is cut into n_ranges
   // contiguous ranges, range r served first by the CTAs resident on SM r: tasks are ordered by (permutation slot,
   // cell), so the CTAs of one SM work on NEIGHBOURING cells at the same time and one after the other -- their near
@@ -648,7 +768,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     __syncthreads();
     FSCL_TICK(W, 1);
     for (int exact = prune ? 0 : 1; exact < 2; exact++) {
-      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms);
+      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms, ring, ring_pos);
       if (threadIdx.x == 0) {
         // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
         // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
@@ -657,8 +777,15 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         // below the best exact candidate (a tie would go to the lower index, hence strictly below);
         // otherwise the pass is repeated without bounds.
         const int bm = W.bmask;
-        int best = -1; double bs = -1.7976931348623157e308;
-        for (int j = 0; j < kCoarse; j++) if (!((bm >> j) & 1) && S[j] > bs) { bs = S[j]; best = j; }
+        int best = -1; double bs = -1.7976931348623157e308, runner = bs;
+        for (int j = 0; j < kCoarse; j++)
+          if (!((bm >> j) & 1)) {
+            if (S[j] > bs) { runner = bs; bs = S[j]; best = j; }
+            else if (S[j] > runner && S[j] < bs) runner = S[j];
+          }
+        // decisions at risk: a non-zero gap of a few ulp of the window null sum (exact ties are resolved as the
+        // reference resolves them; anything larger is beyond the rounding of either side)
+        if (bs - runner > 0.0 && bs - runner < 8.0 * 2.220446049250313e-16 * fabs(M.nsum)) atomicAdd(term_counter + kCtrNearAlpha, 1ull);
         int redo = 0;
         for (int j = 0; j < kNB; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
         s_redo = redo;
@@ -671,11 +798,16 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       if (!s_redo) break;
     }
     const int row = s_row;
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, false, nterms);
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, false, nterms, ring, ring_pos);
     if (threadIdx.x == 0) {
-      double bs = M.clr, la = M.lalpha;
+      double bs = M.clr, la = M.lalpha, runner = -1.7976931348623157e308;
       const int nf = c_alpha.n[row];
-      for (int j = 0; j < nf; j++) if (S[j] > bs) { bs = S[j]; la = c_alpha.la[row][j]; }
+      for (int j = 0; j < nf; j++) {
+        if (S[j] > bs) { runner = bs; bs = S[j]; la = c_alpha.la[row][j]; }
+        else if (S[j] > runner && S[j] < bs) runner = S[j];
+      }
+      const double ulp_n = 2.220446049250313e-16 * fabs(M.nsum);
+      if (bs - runner > 0.0 && bs - runner < 8.0 * ulp_n) atomicAdd(term_counter + kCtrNearAlpha, 1ull);
       M.lalpha = la; M.clr = 2.0 * bs;                // sm-search.c:298 without the null cancellation
       // ---- search_maxpos bookkeeping ----
       int next = -1;
@@ -684,8 +816,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         if (!(flags & kFlagSingle)) next = t.end_pos;
       } else {
         if (step == 1) B = M;
-        else if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M;           // scan-chromosome.c:116
-        else A = M;
+        else {
+          const double gap = fabs(A.clr - B.clr);
+          if (gap > 0.0 && gap < 32.0 * ulp_n) atomicAdd(term_counter + kCtrNearPos, 1ull);
+          if ((A.clr + M.clr) >= (B.clr + M.clr)) B = M;              // scan-chromosome.c:116
+          else A = M;
+        }
         if (B.sweep_pos - A.sweep_pos > P.bp_resl) next = (A.sweep_pos + B.sweep_pos) / 2;
         else if (!(A.clr > B.clr)) A = B;                              // scan-chromosome.c:110
       }

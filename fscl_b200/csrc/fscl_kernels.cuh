@@ -80,6 +80,10 @@ struct TileSet {
   size_t cls_stride;
 };
 
+// device counters of a context (fscl_debug_counters): [0] SNP-terms of COUNT launches, [1] coarse passes repeated exactly,
+// [2..15] phase latencies (-DFSCL_TIMING), [16..143] term histogram (-DFSCL_HIST), then the near-tie counters
+constexpr int kCtrNearAlpha = 144, kCtrNearPos = 145, kDebugCounters = 146;
+
 struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix
 
 struct OutPt {

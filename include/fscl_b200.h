@@ -96,6 +96,12 @@ typedef struct {
   double permute_kernel_ms; /* CUDA-event time of the block-permute kernel */
   int64_t score_launches, permute_launches;
   int64_t kernel_launches;  /* every kernel of this library launched for the context */
+  /* Arithmetic contract: sums are formed in a fixed tree and returned as (N + sum) - N with N the window null
+   * log-likelihood (the reference accumulates onto N, sm-search.c:113), so decisions -- the alpha choice, the bisection
+   * branch, the exceedance test -- equal the reference's except where two candidates differ by a few ulp(N) without being
+   * equal.  These count such decisions (filled by fscl_get_stats; since fscl_create / fscl_reset_stats):            */
+  int64_t near_ties_alpha;     /* grid-evals whose best and second-best alpha candidate differ by 0 < gap < 8 ulp(N)  */
+  int64_t near_ties_position;  /* bisection steps whose two end points differ by 0 < gap < 32 ulp(N)                  */
 } fscl_stats_t;
 
 const char *fscl_last_error(void);

@@ -229,7 +229,7 @@ struct PhaseScratch {
 
 // Bounds of the far tiles for all grid-evals of one cell: sweep positions in [A.sweep_pos, B.sweep_pos],
 // windows between A's and B's (nearest site, window ends and the D3 shift are monotone in the position).
-__device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, const int *__restrict__ tnrun,
+__device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, const int *__restrict__ tnrun, int chr,
                                 const PtS &A, const PtS &B, double (*red)[kMaxFine + 1], PhaseScratch &W) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sa = A.sweep_pos, sb = B.sweep_pos;
@@ -238,13 +238,21 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
   const double *__restrict__ T = P.logT;
   const double inv_step = P.inv_step, offm = P.off_magic;
   const int kclamp = P.n_knots + 1;
+  const int chm_start = P.chr_start[chr], chm_stop = chm_start + P.chr_nsnps[chr] - 1;
   if (threadIdx.x == 0) { W.t0F = t0; W.t1F = t1; W.bmF = 0; }
   __syncthreads();
   for (int t = t0 + (int)threadIdx.x; t <= t1; t += kScanThreads) {
-    const int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
+    int lo = __ldg(P.tile_lo + t), hi = __ldg(P.tile_hi + t);
     const bool ins = (t * kTile >= ws) && (t * kTile + kTile - 1 <= we);
+    // A tile that some window of the cell cuts (a window-edge tile, the first / last tile of the chromosome) can be
+    // bounded as well: whatever subset of its sites a window holds, their sum is below  sum over ALL runs of the
+    // tile of count * max(range maximum, 0), the knot range taken from the part of the tile that lies on this
+    // chromosome (a tile may straddle two chromosomes; positions are sorted within one).
+    const int i0 = max(t * kTile, chm_start), i1 = min(t * kTile + kTile - 1, chm_stop);
+    const bool part = !ins && i0 <= i1 && t * kTile + kTile <= P.n_snps;      // (the padded last tile carries dummy records)
+    if (part) { lo = __ldg(P.pos + i0); hi = __ldg(P.pos + i1); }
     int jb = 0;
-    if (ins) {
+    if (ins || part) {
       // smallest / largest distance of a tile site over the cell's sweep positions (0 when a sweep
       // can fall inside the tile: logt(0) = T[0], the lowest knot the candidate can reach)
       const int dnr = hi < sa ? sa - hi : (lo > sb ? lo - sb : 0);
@@ -273,7 +281,8 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
       }
       if (jb) atomicOr(&W.bmF, (1 << jb) - 1);
     }
-    W.jbF[t - t0] = (unsigned char)jb;
+    if (part) jb = min(jb, 3);        // clipped bounds only for the three widest candidates: they lose by orders of magnitude
+    W.jbF[t - t0] = (unsigned char)(jb | (part && jb ? 0x80 : 0));
   }
   __syncthreads();
   // one warp per tile, lanes over its class runs; pmax = sparse table [level][first knot][class],
@@ -285,7 +294,8 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
     const double *__restrict__ pm = P.pmax;
     const unsigned ncls = (unsigned)P.n_cls, l_stride = ((unsigned)P.n_knots + 2u) * ncls;
     for (int t = t0 + warp; t <= t1; t += kScanWarps) {
-      const int jb = W.jbF[t - t0];
+      const int jbv = W.jbF[t - t0], jb = jbv & 0x7F;
+      const bool clip = (jbv & 0x80) != 0;               // window-edge tile: only the non-negative part of a maximum is a bound
       if (jb == 0) continue;
       const int nr = __ldg(tnrun + t);
       const int *__restrict__ rl = trun + (size_t)t * kTile;
@@ -304,7 +314,8 @@ __device__ void dev_cell_bounds(const Params &P, const int *__restrict__ trun, c
         for (int j = 0; j < kNB; j++) {
           if (j >= jb) break;
           // fmax drops a NaN operand: tables with NaN pieces carry +inf here (host), never pruned
-          ub[j] = fma(cntd, fmax(__ldg(p1[j] + cl), __ldg(p2[j] + cl)), ub[j]);
+          const double mx = fmax(__ldg(p1[j] + cl), __ldg(p2[j] + cl));
+          ub[j] = fma(cntd, clip ? fmax(mx, 0.0) : mx, ub[j]);
         }
       }
     }
@@ -416,8 +427,11 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       int jb = 0;
       if (WITHN) {
         if (bounds_on && t >= W.t0F && t <= W.t1F) {
-          jb = min((int)W.jbF[t - W.t0F], jf);       // jf >= jbF by construction (the cell bound used the largest distance)
-          if (jb) needed = ja > jb;                   // candidates left for the walk
+          const int jbv = W.jbF[t - W.t0F];
+          // jf >= jbF by construction for a whole tile (the cell bound used the largest distance); a tile this
+          // window cuts has jf = 0 and takes the cell's clipped bound as it is
+          jb = ins ? min(jbv & 0x7F, jf) : ((jbv & 0x80) ? (jbv & 0x7F) : 0);
+          if (jb) needed = !ins || ja > jb;           // candidates left for the walk; a cut tile still adds its null sum
         }
       }
       s_tile[t - t0] = ja | (jf << 8) | (ins << 16) | (lu << 17) | (needed << 19) | (jb << 20);
@@ -590,10 +604,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       }
       // alphas whose cut crosses the tile (or a tile cut by the window): per-site predicate;
       // the rows of the kB records of a candidate are in flight together
-      if (jany > jfull) {
+      if (jany > max(jfull, jskip)) {
 #pragma unroll
         for (int j = 0; j < NA; j++) {
-          if (j < jfull) continue;
+          if (j < max(jfull, jskip)) continue;       // candidates a bound stands for are not walked (cut tiles: jfull = 0)
           if (j >= jany) break;
           const double la = c_alpha.la[row][j];
           const int dm = c_alpha.dmax[row][j];
@@ -757,7 +771,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       dev_init_point(P, t.chr, (flags & kFlagSingle) ? t.start_pos : t.end_pos, B);
     }
     __syncthreads();
-    dev_cell_bounds(P, trun, tnrun, A, B, red, W);
+    dev_cell_bounds(P, trun, tnrun, t.chr, A, B, red, W);
   }
   __syncthreads();
   FSCL_TICK(W, 0);

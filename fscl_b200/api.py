@@ -71,7 +71,7 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
            "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima",
            "fscl_perm_fetch_clr", "fscl_perm_project", "fscl_comm_unique_id", "fscl_comm_init_rank", "fscl_comm_init_all",
-           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move", "fscl_debug_histogram"]
+           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move", "fscl_debug_histogram", "fscl_host_replay_gathered"]
 
 _lib = None
 
@@ -115,6 +115,7 @@ def load_library(path=LIB_PATH):
     L.fscl_host_enum_cells.argtypes = [ci, vp, vp, ci, vp, vp, vp, ci]
     L.fscl_host_gen_blocks.argtypes = [ci, vp, vp, vp, ci, vp, ci, vp]
     L.fscl_host_replay_round.argtypes = [vp, vp, ci, vp, ci, ci, vp, vp]
+    L.fscl_host_replay_gathered.argtypes = [vp, vp, ci, vp, ci, C.c_int64, ci, ci, vp, vp]
     L.fscl_host_rng_draws.argtypes = [ci, C.c_uint64, C.c_uint32, C.c_uint32, ci, vp]
     L.fscl_project_pvalues.argtypes = [ci, vp, vp, C.c_double, vp, vp]
     L.fscl_ncx2_sf.argtypes = [ci, vp, C.c_double, vp, vp]
@@ -214,6 +215,19 @@ def host_replay_round(pts, active, matrix, t_first, seed=DEFAULT_SEED, prune=1, 
     r = L.fscl_host_replay_round(pts.ctypes.data, active.ctypes.data, len(active), matrix.ctypes.data,
                                  matrix.shape[0], t_first, C.byref(o),
                                  None if permute_clr is None else permute_clr.ctypes.data)
+    if r < 0:
+        _check(2)
+    return r
+
+
+def host_replay_gathered(pts, active, gathered, world, chunk, R, t_first, seed=DEFAULT_SEED, prune=1, permute_clr=None):
+    """Counting + pruning of one round from all-gathered rows (rank g's rows [q][n_active] at g * chunk)."""
+    L = load_library()
+    active = _i32(active)
+    gathered = np.ascontiguousarray(gathered, dtype=np.float64)
+    o = fscl_permute_opts_t(0, 0.1, 1, 1.0, RNG_PHILOX, seed, prune, 0, 1, 0, 0)
+    r = L.fscl_host_replay_gathered(pts.ctypes.data, active.ctypes.data, len(active), gathered.ctypes.data, world, chunk,
+                                    R, t_first, C.byref(o), None if permute_clr is None else permute_clr.ctypes.data)
     if r < 0:
         _check(2)
     return r

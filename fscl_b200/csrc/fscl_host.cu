@@ -1792,6 +1792,25 @@ extern "C" int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int
   return replay_round(pts, active, (size_t)n_active, matrix, R, t_first, src, o->prune, permute_clr);
 }
 
+// The same for a round whose rows arrive as the library's all-gather delivers them: rank g's rows [q][n_active] at
+// gathered + g * chunk (host statement of replay_kernel's addressing; the 2-rank gloo test drives it)
+extern "C" int fscl_host_replay_gathered(fscl_pt_t *pts, const int32_t *active, int n_active, const double *gathered,
+                                         int world, int64_t chunk, int R, int t_first, const fscl_permute_opts_t *o,
+                                         float *permute_clr) {
+  if (!pts || !active || n_active < 0 || !gathered || R < 0 || !o || world < 1 || chunk < 0) { fail(FSCL_ERR_ARG, "bad argument"); return -1; }
+  if (o->rng_kind != FSCL_RNG_PHILOX) { fail(FSCL_ERR_ARG, "replay needs the counter-based stream"); return -1; }
+  std::vector<double> dense((size_t)R * (size_t)n_active);
+  for (int r = 0; r < R; r++) {
+    int g, q;
+    round_row_owner(t_first, world, r, g, q);
+    if ((int64_t)(q + 1) * n_active > chunk) { fail(FSCL_ERR_ARG, "chunk too small for the round"); return -1; }
+    memcpy(dense.data() + (size_t)r * n_active, gathered + (size_t)g * (size_t)chunk + (size_t)q * n_active, sizeof(double) * (size_t)n_active);
+  }
+  DrawSource src;
+  src.init(o->rng_kind, o->seed);
+  return replay_round(pts, active, (size_t)n_active, dense.data(), R, t_first, src, o->prune, permute_clr);
+}
+
 // 31-bit draws of the two generators (known-answer tests)
 extern "C" int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out) {
   if (!out || n < 0) return fail(FSCL_ERR_ARG, "bad argument");

@@ -1224,11 +1224,9 @@ __global__ void replay_kernel(int na_cap, const int *__restrict__ count_dev, int
   const int s = active[a];
   const double obs = obs_clr[s];
   int p = pp[s], n = pn[s], fin = 0;
-  const int t0m = t_first % stride;
   for (int r = 0; r < R && !fin; r++) {
-    const int g = (t0m + r) % stride;
-    const int first_r = (g - t0m + stride) % stride;       // first row of the round that rank g scored
-    const int q = (r - first_r) / stride;
+    int g, q;
+    round_row_owner(t_first, stride, r, g, q);
     const double clr = matrix[(size_t)g * chunk + (size_t)q * na + a];
     if (scored[r] == 0) scored[r] = 1;                 // benign race: every writer stores 1
     if (clr >= obs) {

@@ -86,6 +86,16 @@ constexpr int kCtrNearAlpha = 144, kCtrNearPos = 145, kDebugCounters = 146;
 
 struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix
 
+// Row r of a round that starts at permutation t_first, sharded over `stride` ranks (rank g scores the permutations
+// t with t % stride == g as its local rows q = 0, 1, ...): which rank scored it, and as which of its rows.
+// One function for the device replay and the host statement of it (tests run the latter over gloo).
+__host__ __device__ inline void round_row_owner(int t_first, int stride, int r, int &g, int &q) {
+  const int t0m = t_first % stride;
+  g = (t0m + r) % stride;
+  const int first_r = (g - t0m + stride) % stride;       // first row of the round that rank g scored
+  q = (r - first_r) / stride;
+}
+
 struct OutPt {
   int chr, nearest, sweep_pos, n_snps, wstart, wend;
   double lalpha, clr, null_logl;

@@ -193,6 +193,10 @@ int fscl_host_gen_blocks(int n_snps, const int32_t *chr, const int32_t *pos, con
                          int t, int32_t *blocks, int max_blocks, int32_t *d7_hits);
 int fscl_host_replay_round(fscl_pt_t *pts, const int32_t *active, int n_active, const double *matrix,
                            int R, int t_first, const fscl_permute_opts_t *opts, float *permute_clr);
+/* the same replay for rows laid out as the library's per-round all-gather delivers them: rank g's rows
+ * [q][n_active] at gathered + g * chunk, rank g owning the permutations t = g (mod world) */
+int fscl_host_replay_gathered(fscl_pt_t *pts, const int32_t *active, int n_active, const double *gathered, int world,
+                              int64_t chunk, int R, int t_first, const fscl_permute_opts_t *opts, float *permute_clr);
 int fscl_host_rng_draws(int rng_kind, uint64_t seed, uint32_t t, uint32_t stream, int n, int32_t *out);
 /* Sweep-model tables built on the device: compute_sweep_model_tables (sm-spline.c:486) with
  * ascbias_adjust_background / ascbias_adjust_expect (asc-bias.c:27,97), pjh/pbk/p_kescape

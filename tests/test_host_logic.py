@@ -168,6 +168,27 @@ def test_sharded_rounds_over_gloo_two_ranks(api, tmp_path):
     assert np.array_equal(a[0], want["permute_p"]) and np.array_equal(a[1], want["permute_n"])
 
 
+def test_all_gathered_rounds_over_gloo_two_ranks(api, tmp_path):
+    """The library's own sharding protocol on the CPU: rank g owns the permutations t = g (mod 2) as rows [q][n_active] of
+    its chunk, ONE all_gather per round (gloo here, NCCL on the GPUs), the replay addresses row r of the round as
+    (rank, local row) with the function the device kernel uses -> identical counts on both ranks, equal to the
+    sequential oracle.  Rounds of 5 permutations: odd round starts and an uneven split (3 + 2 rows) every round."""
+    script = os.path.join(ROOT, "tests", "gloo_worker.py")
+    out = [str(tmp_path / f"g{r}.npy") for r in range(2)]
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2", FSCL_TEST_ROUND="5")
+    procs = [subprocess.Popen([sys.executable, script, out[r], "gather"], env=dict(env, RANK=str(r)), cwd=ROOT)
+             for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    a, b = np.load(out[0]), np.load(out[1])
+    assert np.array_equal(a, b)
+    flat, opt, _ = load_case("unfolded_n40_perm")
+    o = po.Oracle(flat, mode=2)
+    pts0, _ = o.scan(opt["G"])
+    want, _, _, _, _ = o.scan_permute(pts0, 30, opt["G"], o.rng("philox", 5))
+    assert np.array_equal(a[0], want["permute_p"]) and np.array_equal(a[1], want["permute_n"])
+
+
 @pytest.mark.parametrize("kind", ["small50", "asc", "ascnan"])
 def test_piece_maxima_bound_every_spline_value(api, kind):
     """The candidate bounds rest on pmax[l][k][c] >= spline_c(x) - null_c for every x of the knots k .. k+2^l-1

@@ -51,7 +51,8 @@ class fscl_stats_t(C.Structure):
                 ("n_rounds", C.c_int64), ("n_blocks", C.c_int64), ("d7_hits", C.c_int32),
                 ("bound_failures", C.c_int32), ("score_kernel_ms", C.c_double), ("permute_kernel_ms", C.c_double),
                 ("score_launches", C.c_int64), ("permute_launches", C.c_int64),
-                ("kernel_launches", C.c_int64), ("near_ties_alpha", C.c_int64), ("near_ties_position", C.c_int64)]
+                ("kernel_launches", C.c_int64), ("near_ties_alpha", C.c_int64), ("near_ties_position", C.c_int64),
+                ("fine_bound_failures", C.c_int64)]
 
     def asdict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

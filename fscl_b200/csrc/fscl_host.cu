@@ -1886,13 +1886,14 @@ extern "C" int fscl_get_stats(void *ctx, fscl_stats_t *s) {
   Ctx *c = (Ctx *)ctx;
   if (!c || !s) return fail(FSCL_ERR_ARG, "bad argument");
   cudaSetDevice(c->device);
-  unsigned long long redo = 0, near[2] = {0, 0};
+  unsigned long long redo = 0, near[3] = {0, 0, 0};
   CK(cudaStreamSynchronize(c->stream));
   CK(cudaMemcpy(&redo, c->d_terms + 1, sizeof redo, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(near, c->d_terms + kCtrNearAlpha, sizeof near, cudaMemcpyDeviceToHost));
   c->stats.bound_failures = (int32_t)std::min<unsigned long long>(redo, 0x7FFFFFFFull);
   c->stats.near_ties_alpha = (int64_t)near[0];
   c->stats.near_ties_position = (int64_t)near[1];
+  c->stats.fine_bound_failures = (int64_t)near[2];
   *s = c->stats;
   return FSCL_OK;
 }
@@ -1901,7 +1902,7 @@ extern "C" int fscl_reset_stats(void *ctx) {
   if (!c) return fail(FSCL_ERR_ARG, "bad argument");
   cudaSetDevice(c->device);
   cudaMemsetAsync(c->d_terms + 1, 0, sizeof(unsigned long long), c->stream);
-  cudaMemsetAsync(c->d_terms + kCtrNearAlpha, 0, 2 * sizeof(unsigned long long), c->stream);
+  cudaMemsetAsync(c->d_terms + kCtrNearAlpha, 0, 3 * sizeof(unsigned long long), c->stream);
   memset(&c->stats, 0, sizeof c->stats);
   return FSCL_OK;
 }

@@ -206,6 +206,11 @@ struct PhaseScratch {
   unsigned char jbF[kMaxTilesC + 2];    // cell level: leading candidates of the tile that a bound stands for
   double ubF[kNB];                        // cell level: bound sums per candidate over those tiles
   int t0F, t1F, bmF;                    // tile range of the cell's windows; candidates with a bounded tile
+  // fine pass of ONE grid-eval (dev_phase, WITHN = false): the far tiles of its widest candidates are bounded as well
+  unsigned krE[kMaxTilesC + 2][kNBF];   // first knot | extra knots << 16 per (tile, fine candidate)
+  unsigned char jbE[kMaxTilesC + 2];    // leading fine candidates of the tile that a bound stands for
+  double ubE[kNBF];                     // bound sums per fine candidate
+  int bmE;                              // fine candidates with a bounded tile
   int n_list, bmask;
 #ifdef FSCL_TIMING
   long long tacc[16], tlast;            // phase latencies seen by thread 0 (debug builds only)
@@ -355,7 +360,9 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
   double accn = 0.0;
 #pragma unroll
   for (int j = 0; j < NA; j++) acc[j] = 0.0;
-  if (threadIdx.x == 0) W.bmask = 0;
+  if (threadIdx.x == 0) { W.bmask = 0; if (!WITHN) W.bmE = 0; }
+  const bool fine_bounds = !WITHN && use_bound;
+  if (!WITHN) __syncthreads();               // bmE is or-ed by the classifying threads below
   if (na > 0 || WITHN) {
     const int sweep = R.sweep_pos, ws = R.wstart, we = R.wend;
     const unsigned wlen = (unsigned)(we - ws);
@@ -425,6 +432,29 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       // sum of a tile the window cuts; complete tiles take their null sum from tnull
       int needed = (WITHN && !ins) || ja > 0;
       int jb = 0;
+      if (!WITHN && fine_bounds && ins && dnr > 0 && jf > 0) {
+        // Fine pass: a whole tile on one side of the sweep that lies wholly inside the cuts of the first jf fine
+        // candidates and spans at most kLimFine + 1 knots for them is not summed site by site for (a prefix of) those
+        // candidates: its share is bounded from its class runs and the range maxima, exactly as dev_cell_bounds does
+        // for the coarse list, but for THIS sweep position and THIS fine list.  The wide fine candidates of a low
+        // coarse maximum (l_alpha = -10.4: 14 candidates out to 17 Mb, 104 k terms) lose by far and are the bulk of
+        // what the fine passes evaluate; the caller checks  bound + tolerance < best exact  and repeats the pass
+        // exactly otherwise.
+        const double xa = dev_logt(T, dnr), xb = dev_logt(T, dfar);
+        bool open = true;
+#pragma unroll
+        for (int k = 0; k < kNBF; k++) {
+          const double la = c_alpha.la[row][k];
+          const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), (int)kclamp);
+          const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), (int)kclamp);
+          const int ex = max(kb - ka, 0);
+          open = open && k < min(jf, naw) && ex <= kLimFine;
+          if (open) jb = k + 1;
+          W.krE[t - t0][k] = (unsigned)ka | ((unsigned)ex << 16);
+        }
+        if (jb) { atomicOr(&W.bmE, (1 << jb) - 1); needed = ja > jb; }
+      }
+      if (!WITHN) W.jbE[t - t0] = (unsigned char)jb;
       if (WITHN) {
         if (bounds_on && t >= W.t0F && t <= W.t1F) {
           const int jbv = W.jbF[t - W.t0F];
@@ -438,6 +468,53 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     }
     __syncthreads();
     FSCL_TICK(W, (WITHN ? 2 : 7));
+    if (!WITHN && fine_bounds && W.bmE) {
+      // one warp per bounded tile, lanes over its class runs (see dev_cell_bounds)
+      double ub[kNBF];
+#pragma unroll
+      for (int k = 0; k < kNBF; k++) ub[k] = 0.0;
+      const double *__restrict__ pm = P.pmax;
+      const unsigned ncls = (unsigned)P.n_cls, l_stride = ((unsigned)P.n_knots + 2u) * ncls;
+      for (int t = t0 + warp; t <= t1; t += kScanWarps) {
+        const int jb = W.jbE[t - t0];
+        if (jb == 0) continue;
+        const int nr = __ldg(tnrun + t);
+        const int *__restrict__ rl = trun + (size_t)t * kTile;
+        const double *p1[kNBF], *p2[kNBF];
+#pragma unroll
+        for (int k = 0; k < kNBF; k++) {
+          const unsigned kr = W.krE[t - t0][k], ka = kr & 0xFFFF, ex = kr >> 16;
+          const unsigned lv = 31 - __clz(ex + 1);
+          p1[k] = pm + ((size_t)lv * l_stride + (size_t)ka * ncls);
+          p2[k] = pm + ((size_t)lv * l_stride + (size_t)(ka + ex + 1 - (1u << lv)) * ncls);
+        }
+        for (int r = lane; r < nr; r += 32) {
+          const unsigned e = (unsigned)__ldg(rl + r), cl = e & 0xFFFFFu;
+          const double cntd = (double)(e >> 20);
+#pragma unroll
+          for (int k = 0; k < kNBF; k++) {
+            if (k >= jb) break;
+            ub[k] = fma(cntd, fmax(__ldg(p1[k] + cl), __ldg(p2[k] + cl)), ub[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kNBF; k++) {
+        double v = ub[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) red[warp][k] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < kNBF) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
+        W.ubE[threadIdx.x] = v;
+      }
+      if (threadIdx.x == 0) W.bmask = W.bmE & ((1 << na) - 1);
+      __syncthreads();
+    }
     // tiles that need the per-site walk, in order
     if (warp == 0) {
       int cnt = 0;
@@ -665,6 +742,10 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
 #pragma unroll
     for (int w = 0; w < kScanWarps; w++) v += red[w][threadIdx.x];
     double s = (int)threadIdx.x < na ? (N + v) - N : 0.0;
+    if (!WITHN && threadIdx.x < kNBF && ((W.bmask >> threadIdx.x) & 1)) {
+      const double b = W.ubE[threadIdx.x];
+      s = (v + b) + (1e-4 + 1e-9 * (fabs(v) + fabs(b)));
+    }
     if (WITHN && threadIdx.x < kNB && ((W.bmask >> threadIdx.x) & 1)) {
       // bounded candidate: exact share of the walked tiles + bound of the others + tolerance for the
       // rounding of both (the terms are O(1e2), a window has < 2e5 of them)
@@ -812,14 +893,24 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       if (!s_redo) break;
     }
     const int row = s_row;
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, false, nterms, ring, ring_pos);
+    for (int exact = prune ? 0 : 1; exact < 2; exact++) {
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, exact == 0, nterms, ring, ring_pos);
     if (threadIdx.x == 0) {
+      // fine candidates that carry an upper bound for their far tiles (W.bmask) are out of the race when the bound is
+      // strictly below the best exact value -- the coarse maximum included; otherwise the pass is repeated exactly
+      const int bm = W.bmask;
       double bs = M.clr, la = M.lalpha, runner = -1.7976931348623157e308;
       const int nf = c_alpha.n[row];
       for (int j = 0; j < nf; j++) {
+        if ((bm >> j) & 1) continue;
         if (S[j] > bs) { runner = bs; bs = S[j]; la = c_alpha.la[row][j]; }
         else if (S[j] > runner && S[j] < bs) runner = S[j];
       }
+      int redo = 0;
+      for (int j = 0; j < kNBF; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
+      s_redo = redo;
+      if (redo) { atomicAdd(term_counter + kCtrFineRedo, 1ull); }
+      else {
       const double ulp_n = 2.220446049250313e-16 * fabs(M.nsum);
       if (bs - runner > 0.0 && bs - runner < 8.0 * ulp_n) atomicAdd(term_counter + kCtrNearAlpha, 1ull);
       M.lalpha = la; M.clr = 2.0 * bs;                // sm-search.c:298 without the null cancellation
@@ -840,9 +931,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         else if (!(A.clr > B.clr)) A = B;                              // scan-chromosome.c:110
       }
       s_next = next;
+      }   // !redo
     }
     __syncthreads();
     FSCL_TICK(W, 13);
+    if (!s_redo) break;
+    }   // fine pass, bounded then (rarely) exact
     if (s_next < 0) break;
     pos = s_next;
   }

@@ -49,6 +49,14 @@ constexpr int kPermThreads = 1024;
 #endif
 constexpr int kNB = FSCL_NB;     // leading coarse candidates a bound may stand for (dev_cell_bounds)
 constexpr int kLimLast = FSCL_LIM_LAST, kLimMid = FSCL_LIM_MID;   // extra knots a bound may span (dev_cell_bounds)
+#ifndef FSCL_NBF
+#define FSCL_NBF 4
+#endif
+#ifndef FSCL_LIM_FINE
+#define FSCL_LIM_FINE 4
+#endif
+constexpr int kNBF = FSCL_NBF;           // leading FINE candidates a bound may stand for (dev_phase, fine pass)
+constexpr int kLimFine = FSCL_LIM_FINE;  // extra knots such a bound may span
 #ifndef FSCL_DIRECT
 #define FSCL_DIRECT 128
 #endif
@@ -82,7 +90,7 @@ struct TileSet {
 
 // device counters of a context (fscl_debug_counters): [0] SNP-terms of COUNT launches, [1] coarse passes repeated exactly,
 // [2..15] phase latencies (-DFSCL_TIMING), [16..143] term histogram (-DFSCL_HIST), then the near-tie counters
-constexpr int kCtrNearAlpha = 144, kCtrNearPos = 145, kDebugCounters = 146;
+constexpr int kCtrNearAlpha = 144, kCtrNearPos = 145, kCtrFineRedo = 146, kDebugCounters = 147;
 
 struct Task { int slot, chr, start_pos, end_pos, dst; };   // dst: index into the clr matrix
 

@@ -102,6 +102,7 @@ typedef struct {
    * equal.  These count such decisions (filled by fscl_get_stats; since fscl_create / fscl_reset_stats):            */
   int64_t near_ties_alpha;     /* grid-evals whose best and second-best alpha candidate differ by 0 < gap < 8 ulp(N)  */
   int64_t near_ties_position;  /* bisection steps whose two end points differ by 0 < gap < 32 ulp(N)                  */
+  int64_t fine_bound_failures; /* fine passes repeated exactly because a bounded fine candidate could not be excluded  */
 } fscl_stats_t;
 
 const char *fscl_last_error(void);

@@ -15,5 +15,5 @@ for cfg, fn, slots in ((2, synth.config2, 16), (4, synth.config4, 4)):
         t0 = time.perf_counter(); _, st = sc.bench_scan(G, slots); dt = time.perf_counter() - t0
         best = max(best, slots / (st["score_kernel_ms"] * 1e-3))
     terms, _ = sc.bench_scan(G, 1, count_terms=True)
-    print(f"{tag} c{cfg}: {best:8.2f} scans/s (kernel time), {terms/1e9:.3f} G terms/scan, bound failures {sc.stats()['bound_failures']}", flush=True)
+    print(f"{tag} c{cfg}: {best:8.2f} scans/s (kernel time), {terms/1e9:.3f} G terms/scan, bound failures {sc.stats()['bound_failures']} fine {sc.stats()['fine_bound_failures']}", flush=True)
     sc.close()

@@ -1,28 +1,28 @@
 """Phase latencies per grid-eval seen by thread 0 of each CTA.
 
-Needs a library built with -DFSCL_TIMING:
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared -DFSCL_TIMING \\
-       -o build/var/lib_timing.so fscl_b200/csrc/fscl_{kernels,host,tables}.cu
-  FSCL_B200_LIB=$PWD/build/var/lib_timing.so python tools/probe_phases.py
+Needs a library built with -DFSCL_TIMING (tools/build_variant.sh timing):
+  FSCL_B200_LIB=$PWD/build/var/lib_timing.so python tools/probe_phases.py [2|4]
 """
 import sys, ctypes as C, numpy as np
 sys.path.insert(0, '.')
-from fscl_b200 import api, synth
-from oracle import pyoracle as po
-tab, opt = synth.config2()
-flat = po.RefProblem(tab).flatten()
+from fscl_b200 import api, hostref, synth
+cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+tab, opt = {2: synth.config2, 4: synth.config4}[cfg]()
+flat = hostref.load_problem(table=tab, device_tables=True)
 sc = api.Scanner(flat)
-sc.bench_scan(100000, 16)
+G, slots = opt["G"], (16 if cfg == 2 else 2)
+n_cells = len(sc.scan_chromosome(G))
+sc.bench_scan(G, slots)
 buf = (C.c_ulonglong * 16)()
 sc.L.fscl_debug_counters(sc._ctx, buf)
 base = np.array(list(buf), dtype=np.float64)
-sc.bench_scan(100000, 16)
+sc.bench_scan(G, slots)
 sc.L.fscl_debug_counters(sc._ctx, buf)
 d = np.array(list(buf), dtype=np.float64) - base
-names = ["cell bounds (per cell)", "init_scan_result", "C: direct+classify", "C: tile list", "C: walk (thread 0)", "C: wait+reduce sync", "C: combine",
-         "F: direct+classify", "F: tile list", "F: walk (thread 0)", "F: wait+reduce sync", "F: combine", "argmax coarse", "bookkeeping"]
-n_cta = 16000.0
+names = ["cell bounds (per cell)", "init_scan_result", "C: direct+classify(+fine bounds)", "C: tile list", "C: walk (thread 0)", "C: wait+reduce sync", "C: combine",
+         "F: direct+classify(+fine bounds)", "F: tile list", "F: walk (thread 0)", "F: wait+reduce sync", "F: combine", "argmax coarse", "bookkeeping"]
+n_cta = float(slots * n_cells)
 tot = d[2:16].sum()
-print("cycles per CTA: %.0f  (per eval %.0f)" % (tot / n_cta, tot / n_cta / 12))
+print("c%d: cycles per CTA: %.0f  (per eval %.0f)" % (cfg, tot / n_cta, tot / n_cta / 12))
 for i, nm in enumerate(names):
-    print(f"{nm:28s} {d[2+i]/n_cta:10.0f} cycles/CTA  {100*d[2+i]/tot:5.1f}%")
+    print(f"{nm:34s} {d[2+i]/n_cta:10.0f} cycles/CTA  {100*d[2+i]/tot:5.1f}%")

@@ -31,7 +31,10 @@ struct PtS {          // one evaluated scan point, shared by the CTA
 // init_scan_result, scan-chromosome.c:58-101 (window null sum is deferred).  Called by the 32 lanes
 // of one warp: the bisection of search_snppos becomes a 32-way search (4 dependent loads instead of
 // 17 for 200k sites); a sorted array has one answer whatever the probe sequence.
-__device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
+// lo_hint / hi_hint (global site indices, or -1): the answer is known to lie between them -- the bisection of a cell only
+// visits positions between its two current end points, whose sites bracket the new one (nearest site and sweep
+// position are monotone in the requested position).
+__device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R, int lo_hint = -1, int hi_hint = -1) {
   const int lane = threadIdx.x & 31;
   const int start = P.chr_start[chr], n = P.chr_nsnps[chr];
   const int *__restrict__ p = P.pos + start;
@@ -39,6 +42,8 @@ __device__ void dev_init_point(const Params &P, int chr, int pos, PtS &R) {
   // is not below sweep_pos (n if none); index 0 is never probed there either
   const double sp = (double)pos;
   int lo = 1, hi = n;                          // answer in [lo, hi]
+  if (lo_hint >= 0) lo = max(lo, min(lo_hint - start, n));
+  if (hi_hint >= 0) hi = max(lo, min(hi, hi_hint - start));
   while (hi > lo) {
     const int span = hi - lo, step = (span + 31) / 32;
     const int m = lo + lane * step;
@@ -120,6 +125,7 @@ __device__ __forceinline__ void batch_terms_pipelined(double *acc, const double 
 #ifndef FSCL_TMA
 #define FSCL_TMA 0
 #endif
+
 // ---- record streams through shared memory (TMA bulk copies + mbarriers): -DFSCL_TMA=1, NOT the default ----
 // The walk reads the class-bucketed records of a tile (tkey, tpos: 2 x 4 KB, contiguous) exactly once per
 // pass; through the LSU that is two streaming loads per 32 records, every sector an L1 miss and a fill
@@ -648,7 +654,8 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
       }
       // alphas whose cut covers the whole tile: no predicate, no clamp (x <= 4 => knot <= n_knots)
       if (jskip > 0) {
-        // some leading candidates are bounded: the few that are left, one at a time
+        // some leading candidates are bounded: the few that are left, one at a time (grouping them by four, with one
+        // code copy per first candidate, was measured: -1.5 %, the copies cost more than the exposed latencies)
 #pragma unroll
         for (int j = 0; j < NA; j++) {
           if (j < jskip) continue;
@@ -859,7 +866,15 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   int pos = t.start_pos;
   for (int step = 0;; step++) {
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
-    if (threadIdx.x < 32) dev_init_point(P, t.chr, pos, M);
+    // (the two end points were located for the cell bounds already; a mid point lies between the current end points:
+    //  its site index is at least A's nearest site and at most B's nearest site + 1, plus B's D3 shift, which equals
+    //  B.dnear when a shift happened and only loosens the bracket when not)
+    if (threadIdx.x < 32) {
+      if (prune && step == 0) { if (threadIdx.x == 0) M = A; }
+      else if (prune && step == 1) { if (threadIdx.x == 0) M = B; }
+      else if (step >= 2) dev_init_point(P, t.chr, pos, M, A.nearest, B.nearest + 1 + B.dnear);
+      else dev_init_point(P, t.chr, pos, M);
+    }
     __syncthreads();
     FSCL_TICK(W, 1);
     for (int exact = prune ? 0 : 1; exact < 2; exact++) {

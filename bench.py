@@ -264,7 +264,9 @@ def main():
     value = scans / dt
     kern_ms = st["score_kernel_ms"] / max(st["score_launches"], 1)
     achieved_tf = FLOP_PER_TERM * terms_round / (kern_ms * 1e-3) / 1e12
-    bound_failures = sc.stats()["bound_failures"]
+    st_now = sc.stats()
+    bound_failures, fine_failures = st_now["bound_failures"], st_now["fine_bound_failures"]
+    near_ties = (st_now["near_ties_alpha"], st_now["near_ties_position"])
     launches_steps = int(st["kernel_launches"])
 
     # ---- e2e: host buffers through the public API, H2D/D2H inside the timed region.  One step per rank:
@@ -328,7 +330,6 @@ def main():
         p2, st2, _ = sc.scan_permute(obs, args.pruned_perms, G, rng=api.RNG_PHILOX, seed=SEED_PRUNED, prune=1)
         t_pr = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        tasks_all = max_over_ranks(float(st2["n_tasks"])) if world == 1 else None
         tt = torch.tensor([float(st2["n_tasks"]), st2["score_kernel_ms"]], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt)
@@ -407,10 +408,14 @@ def main():
                          "frac": achieved_tf / fp64_peak, "traffic": traffic,
                          "kernel": "scan_cells_kernel", "kernel_ms": kern_ms, "snp_terms_per_launch": int(terms_round),
                          "flop_per_term": FLOP_PER_TERM,
-                         "what": "achieved/frac count only the SNP-terms the kernel EVALUATES; coarse candidates whose sum "
-                                 "is provably below the best exact one are excluded by an upper bound, not summed "
-                                 "(results identical, DESIGN.md 3.1)",
+                         "what": "achieved/frac count only the SNP-terms the kernel EVALUATES; coarse and fine candidates "
+                                 "whose sum is provably below the best exact one are excluded by an upper bound, not summed "
+                                 "(results identical, DESIGN.md 3.1). The excluded terms are the cheapest ones (far tiles, "
+                                 "L1 hits), so every such exclusion lowers frac while it raises scans/s",
                          "coarse_passes_repeated_exactly": int(bound_failures),
+                         "fine_passes_repeated_exactly": int(fine_failures),
+                         "decisions_within_a_few_ulp_of_the_null_sum": {"alpha": int(near_ties[0]), "bisection": int(near_ties[1]),
+                                                                       "of_grid_evals": int(args.steps * R * n_cells * 12)},
                          "grid_evals_per_launch": int(R * n_cells * 12),
                          "peak_source": "FP64 FMA-chain microbenchmark run in this process (MEASURED_PEAKS.json "
                                         "has no FP64 figure; SURVEY.md 8d)",

@@ -354,7 +354,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
                                           const int *__restrict__ trun, const int *__restrict__ tnrun,
                                           const int *__restrict__ icls, PtS &R, int row, double (*red)[kMaxFine + 1], double *S,
                                           PhaseScratch &W, bool use_bound, unsigned long long &nterms, RecRing &ring,
-                                          unsigned &ring_pos) {
+                                          unsigned &ring_pos, int fine_nb = kNBF) {
   int *s_tile = W.tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int na_all = c_alpha.n[row];
@@ -454,7 +454,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           const int ka = min(max(__double2loint(fma(xa + la, inv_step, offm)), 0), (int)kclamp);
           const int kb = min(max(__double2loint(fma(xb + la, inv_step, offm)), 0), (int)kclamp);
           const int ex = max(kb - ka, 0);
-          open = open && k < min(jf, naw) && ex <= kLimFine;
+          open = open && k < min(min(jf, naw), fine_nb) && ex <= kLimFine;
           if (open) jb = k + 1;
           W.krE[t - t0][k] = (unsigned)ka | ((unsigned)ex << 16);
         }
@@ -908,8 +908,10 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       if (!s_redo) break;
     }
     const int row = s_row;
-    for (int exact = prune ? 0 : 1; exact < 2; exact++) {
-    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, exact == 0, nterms, ring, ring_pos);
+    // fine pass with the far tiles of its fine_nb widest candidates bounded; a bounded candidate that cannot be excluded
+    // lowers fine_nb to its index and the pass is repeated (fine_nb = 0: everything exact)
+    for (int fine_nb = prune ? kNBF : 0;;) {
+    dev_phase<kMaxFine, COUNT, false>(P, tkey, tpos, tnull, trun, tnrun, icls, M, row, red, S, W, fine_nb > 0, nterms, ring, ring_pos, fine_nb);
     if (threadIdx.x == 0) {
       // fine candidates that carry an upper bound for their far tiles (W.bmask) are out of the race when the bound is
       // strictly below the best exact value -- the coarse maximum included; otherwise the pass is repeated exactly
@@ -921,8 +923,8 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         if (S[j] > bs) { runner = bs; bs = S[j]; la = c_alpha.la[row][j]; }
         else if (S[j] > runner && S[j] < bs) runner = S[j];
       }
-      int redo = 0;
-      for (int j = 0; j < kNBF; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
+      int redo = 0;                                   // 1 + index of the first bounded candidate that is not excluded
+      for (int j = kNBF - 1; j >= 0; j--) if (((bm >> j) & 1) && !(S[j] < bs)) redo = j + 1;
       s_redo = redo;
       if (redo) { atomicAdd(term_counter + kCtrFineRedo, 1ull); }
       else {
@@ -951,7 +953,8 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     __syncthreads();
     FSCL_TICK(W, 13);
     if (!s_redo) break;
-    }   // fine pass, bounded then (rarely) exact
+    fine_nb = s_redo - 1;
+    }   // fine pass, bounded then (rarely) with fewer bounds
     if (s_next < 0) break;
     pos = s_next;
   }

@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--impl", default="fscl_b200")
     ap.add_argument("--round-perms", type=int, default=4, help="permuted genomes per rank per step")
     ap.add_argument("--pruned-perms", type=int, default=10000, help="-p of the pruned, strong-scaled run")
-    ap.add_argument("--e2e-perms", type=int, default=8, help="permutations per rank of one end-to-end step")
+    ap.add_argument("--e2e-perms", type=int, default=32, help="permutations per rank of one end-to-end step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pruned-run", action="store_true")
     ap.add_argument("--no-cli", action="store_true")

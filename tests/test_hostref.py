@@ -106,3 +106,21 @@ def test_ms_entry_points_follow_the_reference_protocol(host, tmp_path):
     assert bool(again) and again.contents.n_snps == bg.contents.n_snps
     for so in (bg, first, again):
         host.fscl_ms_free(so)
+
+
+@pytest.mark.parametrize("text,why", [
+    ("//\nsegsites: 3\npositions: 0.1 0.2\n010\n", "positions do not match segsites"),
+    ("//\nsegsites: 2\npositions: 0.1 0.2\n0101\n", "haplotype row does not match segsites"),
+    ("//\nsegsites: 2\npositions: 0.1 0.2\n01\nhello\n", "unexpected text"),
+    ("//\npositions: 0.1\n1\n", "positions before segsites"),
+])
+def test_c_ms_reader_rejects_malformed_input(host, tmp_path, text, why):
+    """Errors follow the reference's convention (message on stderr, exit(1)), so the reader is driven in a child process."""
+    import subprocess
+    import sys
+    path = tmp_path / "bad.ms"
+    path.write_text(text)
+    code = ("import sys; sys.path.insert(0, %r); from fscl_b200 import hostref; L = hostref.load_library(); "
+            "L.fscl_ms_read(%r.encode(), 1000, 0, 0, 0)" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(path)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode == 1 and why in r.stderr, (r.returncode, r.stderr[-300:])

@@ -354,6 +354,7 @@ def main():
             assert same, "sharded permutation counts differ from the single-GPU counts"
             extra["pruned_run"]["equals_single_gpu_counts"] = bool(same)
             extra["pruned_run"]["single_gpu_seconds_same_box"] = t_1
+            extra["pruned_run"]["strong_scaling_efficiency"] = t_1 / (world * t_pr)
         barrier()
 
     cpu = None

@@ -72,7 +72,8 @@ EXPORTS = ["fscl_last_error", "fscl_device_count", "fscl_create", "fscl_destroy"
            "fscl_host_rng_draws", "fscl_project_pvalues", "fscl_ncx2_sf", "fscl_build_tables", "fscl_set_error",
            "fscl_set_exact_candidates", "fscl_perm_snapshot", "fscl_perm_seek", "fscl_debug_counters", "fscl_host_piece_maxima",
            "fscl_perm_fetch_clr", "fscl_perm_project", "fscl_comm_unique_id", "fscl_comm_init_rank", "fscl_comm_init_all",
-           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move", "fscl_debug_histogram", "fscl_host_replay_gathered"]
+           "fscl_comm_destroy", "fscl_comm_info", "fscl_comm_move", "fscl_debug_histogram", "fscl_host_replay_gathered",
+           "fscl_set_endpoint_sharing"]
 
 _lib = None
 
@@ -106,6 +107,7 @@ def load_library(path=LIB_PATH):
     L.fscl_bench_scan.argtypes = [vp, ci, ci, ci, vp, vp]
     L.fscl_get_stats.argtypes = [vp, vp]
     L.fscl_set_exact_candidates.argtypes = [vp, ci]
+    L.fscl_set_endpoint_sharing.argtypes = [vp, ci]
     L.fscl_debug_counters.argtypes = [vp, vp]
     L.fscl_debug_histogram.argtypes = [vp, vp]
     L.fscl_reset_stats.argtypes = [vp]
@@ -480,6 +482,11 @@ class Scanner:
         """on: evaluate every coarse alpha candidate site by site (no pruning by bounds); results are
         identical either way (fscl_b200.h), only the work differs."""
         _check(self.L.fscl_set_exact_candidates(self._ctx, 1 if on else 0))
+
+    def set_endpoint_sharing(self, on=True):
+        """off: every cell evaluates both of its end points itself, as search_maxpos does in the reference; on (default):
+        a cell that starts where the previous one ended takes that evaluation over.  Results are identical bit for bit."""
+        _check(self.L.fscl_set_endpoint_sharing(self._ctx, 1 if on else 0))
 
     def stats(self):
         st = fscl_stats_t()

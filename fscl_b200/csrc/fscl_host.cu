@@ -202,6 +202,7 @@ struct Ctx {
   TileSet ts0{}, ts{};                            // observed genome / permutation slots, class-bucketed
   double *d_pmax = nullptr;                       // piece maxima for the candidate bounds
   bool no_prune = false;                          // evaluate every coarse candidate exactly
+  bool no_chain = false;                          // every cell evaluates both end points itself (fscl_set_endpoint_sharing)
   int *d_tile_lo = nullptr, *d_tile_hi = nullptr;
   int max_slots = 0;
   int *d_pcls = nullptr, *d_scratch = nullptr;
@@ -354,6 +355,8 @@ int ensure_slots(Ctx *c, int slots, int set = 0) {
   return FSCL_OK;
 }
 
+static inline int scan_flags(const Ctx *c) { return (c->no_prune ? kFlagNoPrune : 0) | (c->no_chain ? kFlagNoChain : 0); }
+
 // run the scan kernel over c->h_tasks; results land in c->h_out
 int run_tasks(Ctx *c, bool permuted, int flags, bool fetch = true, double *d_clr = nullptr) {
   size_t nt = c->h_tasks.size();
@@ -362,7 +365,7 @@ int run_tasks(Ctx *c, bool permuted, int flags, bool fetch = true, double *d_clr
   if (rc) return rc;
   CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data(), nt * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
   CK(cudaEventRecord(c->ev0, c->stream));
-  launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->ts : c->ts0, (int)nt, flags | (c->no_prune ? kFlagNoPrune : 0),
+  launch_scan(c->P, c->d_tasks, c->d_out, permuted ? c->ts : c->ts0, (int)nt, flags | scan_flags(c),
               c->d_terms, d_clr, c->stream, nullptr, c->d_queue, c->n_sm);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -630,6 +633,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   std::vector<double> pmax;
   build_piece_maxima(coefC.data(), NC, K, p->step, pmax);
   c->no_prune = getenv("FSCL_B200_NO_PRUNE") != nullptr;
+  c->no_chain = getenv("FSCL_B200_NO_ENDPOINT_SHARING") != nullptr;
   c->n_pad = (c->n + kTile - 1) / kTile * kTile;
   const int n_tiles = c->n_pad / kTile;
   std::vector<int> tlo(n_tiles), thi(n_tiles);
@@ -800,7 +804,7 @@ extern "C" int fscl_scan_chromosome(void *ctx, int G, fscl_pt_t *out, int cap, i
     if (hi > lo) {
       CK(cudaMemcpyAsync(c->d_tasks, c->h_tasks.data() + lo, (hi - lo) * sizeof(Task), cudaMemcpyHostToDevice, c->stream));
       CK(cudaEventRecord(c->ev0, c->stream));
-      launch_scan(c->P, c->d_tasks, c->d_out + lo, c->ts0, (int)(hi - lo), kFlagNullSum | (c->no_prune ? kFlagNoPrune : 0),
+      launch_scan(c->P, c->d_tasks, c->d_out + lo, c->ts0, (int)(hi - lo), kFlagNullSum | scan_flags(c),
                   c->d_terms, nullptr, c->stream, nullptr, c->d_queue, c->n_sm);
       c->stats.kernel_launches++;
       CK(cudaGetLastError());
@@ -1053,12 +1057,13 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
   if (S.n_active == 0 || S.t_next > o.n_permute) return FSCL_OK;
   const size_t na = (size_t)S.n_active;
   const int lim = slot_limit(c);
-  // at least 4 permutations per rank and round: the swaps of ONE permutation are a single CTA, so a round
-  // of one would leave most of the GPU idle behind it
-  // ... and enough permutations that EVERY rank launches about 16384 searches once few cells are left
+  // enough permutations that EVERY rank launches about 16384 searches: one per rank while most cells are active (the
+  // genomes of the next round are built under the scan of this one, so a short round costs nothing, and a cell that
+  // finishes inside a round has been searched to its end for nothing: 6.4 % of the searches at 8 GPUs with rounds of 4
+  // per rank), up to 64 once few cells are left
   int R = o.round_perms > 0 ? o.round_perms
                             : (int)std::min<size_t>((size_t)kMaxRoundPerRank * S.stride,
-                                                    std::max<size_t>(4, (16384 + na - 1) / na) * (size_t)S.stride);
+                                                    std::max<size_t>(1, (16384 + na - 1) / na) * (size_t)S.stride);
   R = (R + S.stride - 1) / S.stride * S.stride;
   R = std::min(R, lim * S.stride);
   R = std::min(R, o.n_permute - S.t_next + 1);
@@ -1160,7 +1165,7 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_k0[r & 3], c->stream));
-    launch_scan(c->P, c->d_tasks, nullptr, Q.ts, (int)((size_t)ns * na), c->no_prune ? kFlagNoPrune : 0, c->d_terms,
+    launch_scan(c->P, c->d_tasks, nullptr, Q.ts, (int)((size_t)ns * na), scan_flags(c), c->d_terms,
                 c->d_matrix + (size_t)c->rank * chunk, c->stream, d_ntasks, c->d_queue, c->n_sm);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
@@ -1879,6 +1884,13 @@ extern "C" int fscl_set_exact_candidates(void *ctx, int on) {
   Ctx *c = (Ctx *)ctx;
   if (!c) return fail(FSCL_ERR_ARG, "null context");
   c->no_prune = on != 0;
+  return FSCL_OK;
+}
+
+extern "C" int fscl_set_endpoint_sharing(void *ctx, int on) {
+  Ctx *c = (Ctx *)ctx;
+  if (!c) return fail(FSCL_ERR_ARG, "null context");
+  c->no_chain = on == 0;
   return FSCL_OK;
 }
 

@@ -782,7 +782,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   // pipelined permutation rounds size the launch from a stale (larger) active count; the true task
   // count of the round lives on the device (taskgen_kernel)
   const int n_total = n_tasks_dev ? min(*n_tasks_dev, n_tasks_max) : n_tasks_max;
-  __shared__ PtS A, B, M;
+  __shared__ PtS A, B, M, B0;                // B0: the cell's end point as evaluated (B itself moves during the bisection)
   __shared__ double red[kScanWarps][kMaxFine + 1];
   __shared__ double S[kMaxFine + 1];
   __shared__ int s_row, s_next, s_redo;
@@ -819,10 +819,35 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     asm("mov.u32 %0, %%smid;" : "=r"(smid));
     my_range = (int)(smid % (unsigned)n_ranges);
   }
+  // End points shared by neighbouring cells.  Cell i ends where cell i + 1 starts, and search_maxalpha at a position
+  // does not depend on the cell that asks (the exact sums of the candidates that can win are the same sites in the
+  // same order whatever the cell's bounds exclude), so a CTA that has finished a cell keeps the evaluated end point
+  // and goes on with the next task when that one starts there (same slot, same chromosome), up to kChain cells:
+  // the reference evaluates every interior grid point twice (scan-chromosome.c:103-107 per cell), this kernel once.
+  // The CTA launched for a task that a predecessor takes over leaves at once.  Bit-identical to separate
+  // evaluations (tests: fscl_set_endpoint_sharing(ctx, 0)).
+  const bool chain_on = !queue && !(flags & (kFlagSingle | kFlagNoChain));
+  // Chains shorten towards the end of the task list (kChain, then 4, 2, 1 cells over the last 8192 tasks): the CTAs that
+  // are dispatched last are short ones, so a launch does not end with a few SMs working through long chains.
+  auto chained_to_prev = [&](int i) -> bool {
+    if (!chain_on || i <= 0 || i >= n_total) return false;
+    const int rem = n_total - i;
+    const int len = rem > 8192 ? kChain : (rem > 4096 ? min(kChain, 4) : (rem > 2048 ? min(kChain, 2) : 1));
+    if ((i % len) == 0) return false;
+    const Task p = tasks[i - 1], q = tasks[i];
+    return p.slot == q.slot && p.chr == q.chr && p.end_pos == q.start_pos;
+  };
+  bool chained = false;
   for (int iter = 0;; iter++) {
   int ti;
   if (!queue) {
-    ti = (iter == 0 && (int)blockIdx.x < n_total) ? (int)blockIdx.x : -1;
+    if (iter == 0) {
+      ti = ((int)blockIdx.x < n_total && !chained_to_prev((int)blockIdx.x)) ? (int)blockIdx.x : -1;
+    } else {
+      ti = (int)blockIdx.x + iter;
+      chained = chained_to_prev(ti);
+      if (!chained) ti = -1;
+    }
   } else {
     if (threadIdx.x == 0) {
       int got = -1;
@@ -855,7 +880,8 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   if (prune) {
     // bounds of the far tiles, once for every position the search of this cell can visit
     if (threadIdx.x < 32) {
-      dev_init_point(P, t.chr, t.start_pos, A);
+      if (chained) { if (threadIdx.x == 0) A = B0; }          // located AND evaluated by the previous cell of this CTA
+      else dev_init_point(P, t.chr, t.start_pos, A);
       dev_init_point(P, t.chr, (flags & kFlagSingle) ? t.start_pos : t.end_pos, B);
     }
     __syncthreads();
@@ -863,8 +889,9 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   }
   __syncthreads();
   FSCL_TICK(W, 0);
-  int pos = t.start_pos;
-  for (int step = 0;; step++) {
+  if (!prune && chained && threadIdx.x == 0) A = B0;
+  int pos = chained ? t.end_pos : t.start_pos;
+  for (int step = chained ? 1 : 0;; step++) {
     // ---- search_maxalpha sm-search.c:269-300 at `pos` ----
     // (the two end points were located for the cell bounds already; a mid point lies between the current end points:
     //  its site index is at least A's nearest site and at most B's nearest site + 1, plus B's D3 shift, which equals
@@ -937,7 +964,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         A = M;
         if (!(flags & kFlagSingle)) next = t.end_pos;
       } else {
-        if (step == 1) B = M;
+        if (step == 1) { B = M; B0 = M; }
         else {
           const double gap = fabs(A.clr - B.clr);
           if (gap > 0.0 && gap < 32.0 * ulp_n) atomicAdd(term_counter + kCtrNearPos, 1ull);

@@ -60,6 +60,10 @@ constexpr int kLimFine = FSCL_LIM_FINE;  // extra knots such a bound may span
 #ifndef FSCL_DIRECT
 #define FSCL_DIRECT 128
 #endif
+#ifndef FSCL_CHAIN
+#define FSCL_CHAIN 8
+#endif
+constexpr int kChain = FSCL_CHAIN;       // neighbouring cells one CTA may take in a row, each starting from the evaluated end point of the last
 constexpr int kDirect = FSCL_DIRECT;     // sites either side of the nearest one that narrow-cut candidates are summed from directly
 
 struct Params {
@@ -147,6 +151,7 @@ void launch_fma_peak(double *out, int iters, int grid, cudaStream_t s);
 enum { kFlagSingle = 1,      // evaluate start_pos only (search_maxalpha at a point)
        kFlagNullSum = 2,     // also sum null_tab over the final window
        kFlagCount = 4,       // count the SNP-terms the kernel evaluates (roofline numerator)
-       kFlagNoPrune = 8 };   // evaluate every candidate of the coarse list exactly (no pruning by bounds)
+       kFlagNoPrune = 8,     // evaluate every candidate of the coarse list exactly (no pruning by bounds)
+       kFlagNoChain = 16 };  // every cell evaluates both of its end points itself (no sharing between neighbouring cells)
 
 }  // namespace fscl

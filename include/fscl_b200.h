@@ -224,6 +224,11 @@ int fscl_bench_scan(void *ctx, int large_grid_sp, int n_perm_slots, int count_te
  * evaluated site by site -- the selected alpha, CLR and every later decision are unchanged.
  * on = 1 evaluates every candidate exactly (A/B tests, reference-equivalent term counts). */
 int fscl_set_exact_candidates(void *ctx, int on);
+/* search_maxpos (scan-chromosome.c:103-139) evaluates both end points of every cell, so a scan evaluates each interior
+ * grid point twice.  By default a cell that starts where the previous task of the same genome ended takes that end
+ * point's result over instead of evaluating it again (same position, same sites, same order: bit-identical).
+ * on = 0 makes every cell evaluate both of its end points itself (A/B tests). */
+int fscl_set_endpoint_sharing(void *ctx, int on);
 /* Debug hook: the 16 device counters of the context ([0] SNP-terms of COUNT launches, [1] coarse passes
  * repeated exactly; [2..15] phase latencies in cycles, only filled by a library built with -DFSCL_TIMING). */
 int fscl_debug_counters(void *ctx, unsigned long long *out16);

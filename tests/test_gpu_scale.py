@@ -161,3 +161,36 @@ def test_candidate_pruning_changes_nothing_on_other_shapes(api, shape):
         want, _ = o.scan(G)
         assert np.array_equal(b["sweep_pos"], want["sweep_pos"]) and np.array_equal(b["lalpha"], want["lalpha"])
         assert clr_close(b["clr"], want["clr"]).all()
+
+
+@pytest.mark.parametrize("shape", ["c2", "c4"])
+def test_endpoint_sharing_changes_nothing(api, c2, shape):
+    """A cell that starts where the previous one ended takes that end point's evaluation over (scan_cells_kernel);
+    switched off, every cell evaluates both end points itself as search_maxpos does (scan-chromosome.c:103-107).
+    Every output bit must agree: forward scan, stored permuted CLRs, counts -- with and without a pruned test
+    (late rounds hold isolated cells, early ones whole chromosomes) -- and the shared form must evaluate fewer terms."""
+    if shape == "c2":
+        flat, sc, G = c2
+    else:
+        tab, opt = synth.config4(scale=0.05)
+        flat, G = po.RefProblem(tab).flatten(), opt["G"]
+        sc = api.Scanner(flat)
+    try:
+        sc.set_endpoint_sharing(False)
+        a = sc.scan_chromosome(G)
+        ta, _ = sc.bench_scan(G, 16, count_terms=True)
+        pa, _, ca = sc.scan_permute(a, 24, G, rng=api.RNG_PHILOX, seed=41, prune=0, save_clr=True)
+        qa, _, da = sc.scan_permute(a, 60, G, rng=api.RNG_PHILOX, seed=43, prune=1, save_clr=True)
+        sc.set_endpoint_sharing(True)
+        b = sc.scan_chromosome(G)
+        tb, _ = sc.bench_scan(G, 16, count_terms=True)
+        pb, _, cb = sc.scan_permute(b, 24, G, rng=api.RNG_PHILOX, seed=41, prune=0, save_clr=True)
+        qb, _, db = sc.scan_permute(b, 60, G, rng=api.RNG_PHILOX, seed=43, prune=1, save_clr=True)
+    finally:
+        sc.set_endpoint_sharing(True)
+    assert _same_points(a, b) and _same_points(pa, pb) and _same_points(qa, qb)
+    assert ca.tobytes() == cb.tobytes() and da.tobytes() == db.tobytes()
+    assert (qa["permute_finished"] == 1).any() and (qa["permute_finished"] == 0).any()   # sparse late rounds were run
+    # launches of more than 8192 tasks (16 genomes here, the rounds of 17+ permutations above) hold chains of up to 8
+    # cells; the last 8192 tasks of a launch run in shorter chains and singly (scan_cells_kernel)
+    assert 0.85 * ta < tb < 0.99 * ta

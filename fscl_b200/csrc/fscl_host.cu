@@ -202,6 +202,8 @@ struct Ctx {
   TileSet ts0{}, ts{};                            // observed genome / permutation slots, class-bucketed
   double *d_pmax = nullptr;                       // piece maxima for the candidate bounds
   bool no_prune = false;                          // evaluate every coarse candidate exactly
+  int block_cap = 0;
+  bool round_log = false; int log_R[4] = {0, 0, 0, 0}, log_na[4] = {0, 0, 0, 0};   // FSCL_B200_ROUND_LOG
   bool no_chain = false;                          // every cell evaluates both end points itself (fscl_set_endpoint_sharing)
   int *d_tile_lo = nullptr, *d_tile_hi = nullptr;
   int max_slots = 0;
@@ -634,6 +636,8 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   build_piece_maxima(coefC.data(), NC, K, p->step, pmax);
   c->no_prune = getenv("FSCL_B200_NO_PRUNE") != nullptr;
   c->no_chain = getenv("FSCL_B200_NO_ENDPOINT_SHARING") != nullptr;
+  c->round_log = getenv("FSCL_B200_ROUND_LOG") != nullptr;
+  if (const char *e = getenv("FSCL_B200_BLOCK_CAP")) c->block_cap = std::max(1, atoi(e));
   c->n_pad = (c->n + kTile - 1) / kTile * kTile;
   const int n_tiles = c->n_pad / kTile;
   std::vector<int> tlo(n_tiles), thi(n_tiles);
@@ -988,6 +992,28 @@ static int slot_limit(const Ctx *c) {
   return (int)std::max<size_t>(1, std::min<size_t>(kPinSlots, kSlotMemory / 2 / slot_bytes));
 }
 
+// Block-list capacity per permutation on the device.  A permutation of c4 (3 M sites, -b 0.1 blocks per Mb) has about
+// 3 000 blocks; a list that does not fit is flagged by gen_blocks_kernel and the round's lists are drawn on the host
+// instead (same draws), so the capacity is a speed matter only.  (Round 2 first sized it n/4 + 1024 per permutation
+// and grew the buffer whenever a round had more permutations than any before: 126 re-allocations of up to 770 MB in
+// a c4 -p 10000 run, 5 s of its 21 s.)
+static int block_list_stride(const Ctx *c) {
+  if (c->block_cap > 0) return c->block_cap;                 // FSCL_B200_BLOCK_CAP (tests of the overflow path)
+  return std::min(c->n / 4 + 1024, std::max(65536, c->n / 32));
+}
+
+static int ensure_block_lists(Ctx *c, int set, int slots) {
+  SlotRef Q = slot_set(c, set);
+  const size_t need = (size_t)slots * (size_t)block_list_stride(c);
+  if (need <= Q.blocks_cap) return FSCL_OK;
+  CK(cudaStreamSynchronize(c->prep));
+  if (Q.blocks) dev_free(Q.blocks, c->prep);
+  Q.blocks = nullptr; Q.blocks_cap = 0;
+  CK(dev_malloc(&Q.blocks, need * sizeof(int4)));
+  Q.blocks_cap = need;
+  return FSCL_OK;
+}
+
 static int device_begin(Ctx *c) {
   PermState &S = c->perm;
   const int n = S.n_pts;
@@ -1027,7 +1053,11 @@ static int device_begin(Ctx *c) {
   if (S.o.round_perms > 0) want = std::min(std::min(slot_limit(c), kPinSlots), (S.o.round_perms + S.stride - 1) / S.stride);
   want = std::max(want, 1);
   rc = ensure_slots(c, want, 0); if (rc) return rc;
-  if ((long)S.o.n_permute + 1 > (long)want * S.stride) { rc = ensure_slots(c, want, 1); if (rc) return rc; }
+  rc = ensure_block_lists(c, 0, want); if (rc) return rc;
+  if ((long)S.o.n_permute + 1 > (long)want * S.stride) {
+    rc = ensure_slots(c, want, 1); if (rc) return rc;
+    rc = ensure_block_lists(c, 1, want); if (rc) return rc;
+  }
   return FSCL_OK;
 }
 
@@ -1038,6 +1068,13 @@ static int engine_collect(Ctx *c, long upto) {
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, c->ev_k0[S.collected & 3], c->ev_k1[S.collected & 3]));
     c->stats.score_kernel_ms += ms;
+    if (c->round_log) {
+      // FSCL_B200_ROUND_LOG=1: per round, the scan kernel's time and the idle time of the scan stream before it
+      float gap = 0;
+      if (S.collected > 0 && cudaEventElapsedTime(&gap, c->ev_k1[(S.collected - 1) & 3], c->ev_k0[S.collected & 3]) != cudaSuccess) { cudaGetLastError(); gap = -1; }
+      fprintf(stderr, "fscl round %ld R %d active<= %d scan_ms %.3f gap_ms %.3f\n", S.collected, c->log_R[S.collected & 3],
+              c->log_na[S.collected & 3], ms, gap);
+    }
   }
   return FSCL_OK;
 }
@@ -1105,14 +1142,8 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
   if (ns > 0) {
     // ---- prep stream: the permuted genomes of this round ----
     if (c->set_used[set]) CK(cudaStreamWaitEvent(c->prep, c->ev_scan[set], 0));      // the scan of round r-2 read this set
-    const int stride = c->n / 4 + 1024;                       // block-list capacity per permutation
-    if ((size_t)ns_max * stride > Q.blocks_cap) {
-      CK(cudaStreamSynchronize(c->prep));
-      if (Q.blocks) dev_free(Q.blocks, c->prep);
-      Q.blocks = nullptr; Q.blocks_cap = 0;
-      CK(dev_malloc(&Q.blocks, (size_t)ns_max * stride * sizeof(int4)));
-      Q.blocks_cap = (size_t)ns_max * stride;
-    }
+    const int stride = block_list_stride(c);                  // block-list capacity per permutation
+    rc = ensure_block_lists(c, set, ns_max); if (rc) return rc;      // sized at begin: no allocation between rounds
     std::vector<int> starts(ns);
     for (int q = 0; q < ns; q++) starts[q] = q * stride;
     CK(cudaMemcpyAsync(d_tl, tl.data(), sizeof(int) * ns, cudaMemcpyHostToDevice, c->prep));
@@ -1178,6 +1209,7 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
     CK(cudaEventRecord(c->ev_k1[r & 3], c->stream));
   }
   S.R = R; S.na_round = (int)na; S.ns_round = ns; S.chunk = chunk;
+  c->log_R[r & 3] = R; c->log_na[r & 3] = (int)na;
   *R_out = R;
   return FSCL_OK;
 }

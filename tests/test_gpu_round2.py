@@ -346,3 +346,18 @@ def test_persistent_scan_gives_identical_results(api, monkeypatch):
     pb, _, cb = b_sc.scan_permute(obs_b[::7], 12, G // 20, save_clr=True, rng=api.RNG_PHILOX, seed=3, prune=0)
     assert len(obs_a) > 600 and obs_a.tobytes() == obs_b.tobytes()
     assert pa.tobytes() == pb.tobytes() and np.array_equal(ca, cb)
+
+
+def test_block_list_overflow_falls_back_to_host_draws(api, monkeypatch):
+    """The device block lists have a fixed capacity per permutation (sized once at the start of a test); a list that
+    does not fit is flagged by gen_blocks_kernel and the round's lists are drawn on the host from the same counter-based
+    stream.  FSCL_B200_BLOCK_CAP=8 forces that path for every round: counts and stored CLRs must not change."""
+    tab, flat, G = problem("mid100")
+    a_sc = api.Scanner(flat)
+    obs = a_sc.scan_chromosome(G)
+    pa, sa, ca = a_sc.scan_permute(obs, 40, G, save_clr=True, rng=api.RNG_PHILOX, seed=8, prune=1)
+    monkeypatch.setenv("FSCL_B200_BLOCK_CAP", "8")
+    b_sc = api.Scanner(flat)
+    pb, sb, cb = b_sc.scan_permute(obs, 40, G, save_clr=True, rng=api.RNG_PHILOX, seed=8, prune=1)
+    assert sa["n_blocks"] > 40 * 8                             # the lists are longer than the forced capacity
+    assert pa.tobytes() == pb.tobytes() and np.array_equal(ca, cb)

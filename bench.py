@@ -341,8 +341,10 @@ def main():
             "searches_needed": int(needed), "wasted_search_fraction": float(tt[0].item()) / needed - 1.0,
             "rounds": int(st2["n_rounds"]), "scan_kernel_ms_sum_over_ranks": float(tt[1].item()),
             "cells_finished": int(p2["permute_finished"].sum()), "cells": n_cells,
-            "limiter": "late rounds: few active cells x <= 64 permutations per rank and round; each round pays the "
-                       "serial block-swap kernel (one CTA per permutation) and re-buckets whole genomes"}
+            "limiter": "the scan kernel (seconds ~ scan_kernel_ms / n_gpus: rounds follow each other without idle "
+                       "time on the scan stream); late rounds (a few hundred active cells x up to 64 permutations per "
+                       "rank) run at 420 instead of 520 searches/ms because building up to 64 whole permuted genomes "
+                       "per round shares the SMs with the scan"}
         if world > 1 and rank == 0:
             # N-GPU counts must equal the 1-GPU counts: the same test, unsharded, on rank 0's GPU
             s1 = api.Scanner(flat, device=local)
@@ -399,6 +401,9 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(R),
             "grid_evals_per_sec": value * n_cells * 12,
+            "grid_evals_note": "12 per cell as search_maxpos counts them (scan-chromosome.c:103-139); a cell that starts "
+                               "where the previous one ended takes that end point's evaluation over, so about 11.1 per "
+                               "cell are computed (bit-identical, fscl_set_endpoint_sharing)",
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "what": f"per rank and step: Scanner(pinned host arrays) + scan_chromosome (cells sharded) + scan_permute("
                             f"{e2e_perms} x {world} permutations, sharded, no pruning) + counters to host",

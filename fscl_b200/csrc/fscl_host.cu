@@ -697,7 +697,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   P.inv_step = 1.0 / p->step; P.off_magic = 20.0 / p->step - 0.5 + 6755399441055744.0;
   P.pos = c->d_pos; P.chr_start = c->d_chr_start; P.chr_nsnps = c->d_chr_nsnps;
   P.coefC = c->d_coefC; P.row_doubles = (K + 2) * 4; P.tile_lo = c->d_tile_lo; P.tile_hi = c->d_tile_hi; P.logT = c->d_logT; P.null_tab = c->d_null; P.pmax = c->d_pmax;
-  launch_bucket(c->n, c->n_pad, c->d_cls0, 0, c->d_pos, c->d_null, c->ts0, 1, c->stream);
+  launch_bucket(c->n, c->n_pad, c->P.n_cls, c->d_cls0, 0, c->d_pos, c->d_null, c->ts0, 1, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(c->stream));
@@ -861,7 +861,7 @@ static int apply_blocks(Ctx *c, int n_slots) {
   launch_permute(c->n, c->d_cls0, c->d_pcls, c->d_scratch, c->d_blocks, c->d_blkoff, c->d_blkcnt, n_slots, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
-  launch_bucket(c->n, c->n_pad, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->ts,
+  launch_bucket(c->n, c->n_pad, c->P.n_cls, c->d_pcls, (size_t)c->n, c->d_pos, c->d_null, c->ts,
                 n_slots, c->stream);
   c->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -1184,7 +1184,7 @@ static int device_round_score(Ctx *c, int *R_out, int *n_active_out) {
     launch_permute(c->n, c->d_cls0, Q.pcls, Q.scratch, Q.blocks, Q.blkoff, Q.blkcnt, ns, c->prep, d_cnt);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
-    launch_bucket(c->n, c->n_pad, Q.pcls, (size_t)c->n, c->d_pos, c->d_null, Q.ts, ns, c->prep, d_cnt);
+    launch_bucket(c->n, c->n_pad, c->P.n_cls, Q.pcls, (size_t)c->n, c->d_pos, c->d_null, Q.ts, ns, c->prep, d_cnt);
     c->stats.kernel_launches++;
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev_prep[set], c->prep));

@@ -1,4 +1,5 @@
 // fscl_kernels.cu -- sm_100a kernels (see fscl_kernels.cuh for the reference map).
+#include <cstdlib>
 #include "fscl_kernels.cuh"
 #include "fscl_ncx2.cuh"
 
@@ -1191,9 +1192,113 @@ bucket_kernel(int n, int n_pad, const int *__restrict__ cls_all, size_t cls_stri
   }
 }
 
-void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
+// The same tiles by a counting sort, ONE WARP per tile (the default when the per-class counters fit shared memory):
+// a site's place is  first place of its class + sites of that class before it in the tile.  The warp takes the tile in
+// index order, 32 sites at a time: MATCH.ANY groups the lanes of equal class, the group's first lane adds the group to the
+// class counter, a lane's rank is the counter before the chunk + the group members below it -- stable by construction.
+// A scan over the counters gives the first places and, from the non-empty classes, the run list directly; keys and
+// positions go through a 4 KB staging row so that the global writes are coalesced.  No network, no CTA barrier:
+// about 2.5 k warp instructions per tile against 55 compare-exchange steps of 1024 keys (the bitonic kernel above took
+// 6 us of an SM per tile and was most of what a late round of a pruned test pays for its <= 64 new genomes).
+// The tile's null sum keeps the bitonic kernel's order of additions (strided partial sums of 128 threads, shuffle trees,
+// four warp sums in order), so both kernels write the same bits.
+constexpr int kCountWarps = 4;
+__global__ void __launch_bounds__(kCountWarps * 32)
+bucket_count_kernel(int n, int n_pad, int n_cls, const int *__restrict__ cls_all, size_t cls_stride,
+                    const int *__restrict__ pos, const double *__restrict__ null_tab, int *__restrict__ tkey_all,
+                    int *__restrict__ tpos_all, double *__restrict__ tnull_all, int *__restrict__ trun_all,
+                    int *__restrict__ tnrun_all, const int *__restrict__ skip_if_zero) {
+  if (skip_if_zero && *skip_if_zero == 0) return;
+  extern __shared__ int bsm[];
+  constexpr unsigned full = 0xFFFFFFFFu;
+  constexpr int IT = kTile / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int tile = blockIdx.x * kCountWarps + warp, slot = blockIdx.y;
+  if (tile >= n_pad / kTile) return;                          // (warps are independent: no CTA barrier below)
+  int *cnt = bsm + (size_t)warp * (n_cls + kTile);            // per-class counters, then first places
+  int *stage = cnt + n_cls;                                   // kTile ints
+  const int *cls = cls_all + (size_t)slot * cls_stride;
+  const int base = tile * kTile;
+  for (int c = lane; c < n_cls; c += 32) cnt[c] = 0;
+  __syncwarp();
+  int cl[IT], rk[IT];
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    const int gi = base + it * 32 + lane;
+    const int c = gi < n ? __ldg(cls + gi) : 0;              // padding sorts as class 0 behind the real sites of class 0
+    const unsigned m = __match_any_sync(full, c);
+    const int before = cnt[c];
+    __syncwarp();
+    if (lane == __ffs(m) - 1) cnt[c] = before + __popc(m);
+    __syncwarp();
+    cl[it] = c; rk[it] = before + __popc(m & ((1u << lane) - 1u));
+  }
+  // first place of every class (exclusive scan of the counters) + run list of the non-empty classes, in class order
+  int *trun = trun_all + (size_t)slot * n_pad + base;
+  int place = 0, nrun = 0;
+  for (int c0 = 0; c0 < n_cls; c0 += 32) {
+    const int c = c0 + lane;
+    const int v = c < n_cls ? cnt[c] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(full, inc, o); if (lane >= o) inc += t; }
+    const unsigned nz = __ballot_sync(full, v > 0);
+    if (v > 0) trun[nrun + __popc(nz & ((1u << lane) - 1u))] = (int)((unsigned)c | ((unsigned)v << 20));
+    if (c < n_cls) cnt[c] = place + inc - v;
+    place += __shfl_sync(full, inc, 31);
+    nrun += __popc(nz);
+  }
+  if (lane == 0) tnrun_all[(size_t)slot * (n_pad / kTile) + tile] = nrun;
+  __syncwarp();
+  int *tkey = tkey_all + (size_t)slot * n_pad + base, *tpos = tpos_all + (size_t)slot * n_pad + base;
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    rk[it] += cnt[cl[it]];                                    // final place inside the tile
+    stage[rk[it]] = (int)((unsigned)cl[it] | ((unsigned)(it * 32 + lane) << 20));
+  }
+  __syncwarp();
+  for (int e = lane; e < kTile; e += 32) tkey[e] = stage[e];
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    const int gi = base + it * 32 + lane;
+    stage[rk[it]] = gi < n ? __ldg(pos + gi) : 0;
+  }
+  __syncwarp();
+  for (int e = lane; e < kTile; e += 32) tpos[e] = stage[e];
+  // null log-likelihood of the tile in bucket_kernel's order of additions: thread q * 32 + lane of its 128 threads summed
+  // the sites e = q * 32 + lane + kBucketThreads * r, r = 0, 1, ...; then a shuffle tree per warp q; then the warp sums in order
+  constexpr int NW = kBucketThreads / 32;                     // warps of the bitonic kernel; IT = kBucketKeys * NW
+  double tsum = 0.0;
+#pragma unroll
+  for (int q = 0; q < NW; q++) {
+    double ns = 0.0;
+#pragma unroll
+    for (int r = 0; r < kBucketKeys; r++) {
+      const int it = NW * r + q;
+      if (base + it * 32 + lane < n) ns += __ldg(null_tab + cl[it]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ns += __shfl_xor_sync(full, ns, o);
+    tsum += ns;
+  }
+  if (lane == 0) tnull_all[(size_t)slot * (n_pad / kTile) + tile] = tsum;
+}
+
+void launch_bucket(int n, int n_pad, int n_cls, const int *cls_all, size_t cls_stride, const int *pos,
                    const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s, const int *skip_if_zero) {
   if (n_slots <= 0) return;
+  const bool use_bitonic = getenv("FSCL_B200_BITONIC_BUCKETS") != nullptr;      // A/B tests
+  const size_t smem = (size_t)kCountWarps * ((size_t)n_cls + kTile) * sizeof(int);
+  if (!use_bitonic && n_cls < (1 << 20) && smem <= 200 * 1024 &&
+      (smem <= 48 * 1024 ||        // (the attribute is per device: set on every launch that needs it, a host-side table write)
+       cudaFuncSetAttribute(bucket_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess)) {
+    dim3 grid((n_pad / kTile + kCountWarps - 1) / kCountWarps, n_slots);
+    bucket_count_kernel<<<grid, kCountWarps * 32, smem, s>>>(n, n_pad, n_cls, cls_all, cls_stride, pos, null_tab, ts.key, ts.pos,
+                                                             ts.tnull, ts.run, ts.nrun, skip_if_zero);
+    return;
+  }
+  cudaGetLastError();
   dim3 grid(n_pad / kTile, n_slots);
   bucket_kernel<<<grid, kBucketThreads, 0, s>>>(n, n_pad, cls_all, cls_stride, pos, null_tab, ts.key, ts.pos,
                                           ts.tnull, ts.run, ts.nrun, skip_if_zero);

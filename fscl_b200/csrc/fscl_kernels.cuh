@@ -126,7 +126,7 @@ void upload_alpha_tables(const AlphaTables &t);
 void launch_scan(const Params &P, const Task *tasks, OutPt *out, const TileSet &ts, int n_tasks, int flags,
                  unsigned long long *term_counter, double *clr_matrix, cudaStream_t s,
                  const int *n_tasks_dev = nullptr, int *queue = nullptr, int n_sm = 0);
-void launch_bucket(int n, int n_pad, const int *cls_all, size_t cls_stride, const int *pos,
+void launch_bucket(int n, int n_pad, int n_cls, const int *cls_all, size_t cls_stride, const int *pos,
                    const double *null_tab, const TileSet &ts, int n_slots, cudaStream_t s,
                    const int *skip_if_zero = nullptr);
 void launch_permute(int n, const int *cls0, int *pcls_all, int *scratch_all, const int4 *blocks,

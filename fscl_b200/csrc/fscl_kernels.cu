@@ -396,7 +396,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     // the cell-level bounds stand for their candidates' whole share of a tile: usable when none of
     // those candidates is summed directly (windows of at least a few thousand sites)
     const bool bounds_on = WITHN && use_bound && W.bmF && jd >= min(na, kNB);
-    if (bounds_on && threadIdx.x == 0) W.bmask = W.bmF & ((1 << na) - 1);
+    if (bounds_on && threadIdx.x == 0) W.bmask = W.bmF & ((1 << na) - 1) & ((1 << fine_nb) - 1);
     if (jd < na) {
       for (int i = iL + (int)threadIdx.x; i <= iR; i += kScanThreads) {
         const int dd = __ldg(P.pos + i) - sweep, d = dd < 0 ? -dd : dd;
@@ -467,7 +467,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
           const int jbv = W.jbF[t - W.t0F];
           // jf >= jbF by construction for a whole tile (the cell bound used the largest distance); a tile this
           // window cuts has jf = 0 and takes the cell's clipped bound as it is
-          jb = ins ? min(jbv & 0x7F, jf) : ((jbv & 0x80) ? (jbv & 0x7F) : 0);
+          jb = min(ins ? min(jbv & 0x7F, jf) : ((jbv & 0x80) ? (jbv & 0x7F) : 0), fine_nb);   // (coarse pass: fine_nb = bounded candidates allowed)
           if (jb) needed = !ins || ja > jb;           // candidates left for the walk; a cut tile still adds its null sum
         }
       }
@@ -905,8 +905,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
     }
     __syncthreads();
     FSCL_TICK(W, 1);
-    for (int exact = prune ? 0 : 1; exact < 2; exact++) {
-      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, exact == 0, nterms, ring, ring_pos);
+    // coarse pass with the cell's bounds standing for (a prefix of) its coarse_nb widest candidates; a bounded candidate
+    // that cannot be excluded lowers coarse_nb to its index -- it and the narrower ones are then summed exactly, the wider
+    // ones keep their bounds -- and the pass is repeated (coarse_nb = 0: everything exact).  At a sweep it is typically
+    // l_alpha = -12.8 that wins; the three widest candidates (82 % of the reference's terms) still need no exact sum.
+    for (int coarse_nb = prune ? kNB : 0;;) {
+      dev_phase<kCoarse, COUNT, true>(P, tkey, tpos, tnull, trun, tnrun, icls, M, kCoarse, red, S, W, coarse_nb > 0, nterms, ring, ring_pos, coarse_nb);
       if (threadIdx.x == 0) {
         // strict '>' from -DBL_MAX keeps the first maximum and never selects a NaN
         // (sm-search.c:273,281); nothing selected leaves lalpha = LOG_AD_MAX
@@ -924,8 +928,8 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
         // decisions at risk: a non-zero gap of a few ulp of the window null sum (exact ties are resolved as the
         // reference resolves them; anything larger is beyond the rounding of either side)
         if (bs - runner > 0.0 && bs - runner < 8.0 * 2.220446049250313e-16 * fabs(M.nsum)) atomicAdd(term_counter + kCtrNearAlpha, 1ull);
-        int redo = 0;
-        for (int j = 0; j < kNB; j++) if (((bm >> j) & 1) && !(S[j] < bs)) redo = 1;
+        int redo = 0;                                 // 1 + index of the first bounded candidate that is not excluded
+        for (int j = kNB - 1; j >= 0; j--) if (((bm >> j) & 1) && !(S[j] < bs)) redo = j + 1;
         s_redo = redo;
         if (redo) atomicAdd(term_counter + 1, 1ull);
         M.clr = bs; M.lalpha = best < 0 ? 4.0 : c_alpha.la[kCoarse][best];
@@ -934,6 +938,7 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
       __syncthreads();
       FSCL_TICK(W, 12);
       if (!s_redo) break;
+      coarse_nb = s_redo - 1;
     }
     const int row = s_row;
     // fine pass with the far tiles of its fine_nb widest candidates bounded; a bounded candidate that cannot be excluded

@@ -12,6 +12,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-cli --pruned-perms 60 --e2e-perms 2 > $O/r02_launches_run.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:scan_cells -s 3 -c 1 -o $O/r02_scan_c4 -f \
     python tools/ncu_target.py 4 1 > $O/ncu_r02_scan_c4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bucket_count -s 1 -c 1 -o $O/r02_bucket_count -f \
+    python tools/ncu_target.py 4 1 > $O/ncu_r02_bucket_count.log 2>&1
 if [ "$1" = "all" ]; then      # the captures of the other kernels are 57 MB: on request only (gpurun returns at most 64 MB)
 python tools/ncu_target.py 2 4 300 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on \

@@ -400,6 +400,7 @@ __device__ __forceinline__ void dev_phase(const Params &P, const int *__restrict
     if (jd < na) {
       for (int i = iL + (int)threadIdx.x; i <= iR; i += kScanThreads) {
         const int dd = __ldg(P.pos + i) - sweep, d = dd < 0 ? -dd : dd;
+        if (d > c_alpha.dmax[row][jd]) continue;            // beyond the widest of these cuts (they shrink with j): most of the 2 * kDirect sites
         const double x0 = dev_logt(T, d);
         const char *cr = coef + (size_t)__ldg(icls + i) * rowbytes;
 #pragma unroll

@@ -323,7 +323,9 @@ def main():
     # ---- the configuration as quoted: -p 10000 with stochastic pruning, strong-scaled over the ranks
     extra = {}
     if not args.no_pruned_run:
-        sc.scan_permute(obs, 63, G, rng=api.RNG_PHILOX, seed=SEED_PRUNED, prune=1)       # grows both slot sets to their full size
+        # untimed: a short test that grows both slot sets of every rank to their full size (64 permuted genomes per rank,
+        # 7.7 GB from the stream-ordered pool: a once-per-process cost of about a second)
+        sc.scan_permute(obs, 64 * world - 1, G, rng=api.RNG_PHILOX, seed=SEED_PRUNED, prune=1)
         sc.reset_stats()
         barrier()
         t0 = time.perf_counter()
@@ -348,6 +350,7 @@ def main():
         if world > 1 and rank == 0:
             # N-GPU counts must equal the 1-GPU counts: the same test, unsharded, on rank 0's GPU
             s1 = api.Scanner(flat, device=local)
+            s1.scan_permute(obs, 63, G, rng=api.RNG_PHILOX, seed=SEED_PRUNED, prune=1)     # untimed: its slot sets at full size too
             t0 = time.perf_counter()
             p1, _, _ = s1.scan_permute(obs, args.pruned_perms, G, rng=api.RNG_PHILOX, seed=SEED_PRUNED, prune=1)
             t_1 = time.perf_counter() - t0

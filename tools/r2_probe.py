@@ -10,6 +10,7 @@ ap.add_argument("--scale", type=float, default=1.0)
 ap.add_argument("--perms", type=int, default=1000)
 ap.add_argument("--slots", type=int, default=4)
 ap.add_argument("--host-tables", action="store_true")
+ap.add_argument("--reps", type=int, default=2)
 a = ap.parse_args()
 t0 = time.time()
 tab, opt = {2: synth.config2, 3: synth.config3, 4: synth.config4, 5: synth.config5}[a.config](scale=a.scale)
@@ -25,7 +26,7 @@ t0 = time.time(); sc.bench_scan(G, a.slots); t_b = time.time() - t0
 t0 = time.time(); sc.bench_scan(G, a.slots); t_b = time.time() - t0
 out = {"workload": f"c{a.config} x {a.scale}: {len(flat['pos'])} SNPs, {len(flat['chr_start'])} chr, {len(flat['null_tab'])} classes, {len(obs)} cells, -G {G}",
        "synth_s": t_syn, "host_prep_s": t_prep, "forward_scan_s": t_fwd, "permuted_scans_per_s_resident": a.slots / t_b}
-for rep in range(2):
+for rep in range(a.reps):
     sc.reset_stats()
     t0 = time.time()
     pts, st, _ = sc.scan_permute(obs, a.perms, G, rng=api.RNG_PHILOX, seed=4, prune=1, keep_clr=1)

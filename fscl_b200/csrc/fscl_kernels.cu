@@ -829,12 +829,12 @@ scan_cells_kernel(const __grid_constant__ Params P, const Task *__restrict__ tas
   // The CTA launched for a task that a predecessor takes over leaves at once.  Bit-identical to separate
   // evaluations (tests: fscl_set_endpoint_sharing(ctx, 0)).
   const bool chain_on = !queue && !(flags & (kFlagSingle | kFlagNoChain));
-  // Chains shorten towards the end of the task list (kChain, then 4, 2, 1 cells over the last 8192 tasks): the CTAs that
+  // Chains shorten towards the end of the task list (kChain, then 4, 2, 1 cells over the last kChainRamp = 8192 tasks): the CTAs that
   // are dispatched last are short ones, so a launch does not end with a few SMs working through long chains.
   auto chained_to_prev = [&](int i) -> bool {
     if (!chain_on || i <= 0 || i >= n_total) return false;
     const int rem = n_total - i;
-    const int len = rem > 8192 ? kChain : (rem > 4096 ? min(kChain, 4) : (rem > 2048 ? min(kChain, 2) : 1));
+    const int len = rem > kChainRamp ? kChain : (rem > kChainRamp / 2 ? min(kChain, 4) : (rem > kChainRamp / 4 ? min(kChain, 2) : 1));
     if ((i % len) == 0) return false;
     const Task p = tasks[i - 1], q = tasks[i];
     return p.slot == q.slot && p.chr == q.chr && p.end_pos == q.start_pos;

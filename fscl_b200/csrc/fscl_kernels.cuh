@@ -63,6 +63,10 @@ constexpr int kLimFine = FSCL_LIM_FINE;  // extra knots such a bound may span
 #ifndef FSCL_CHAIN
 #define FSCL_CHAIN 8
 #endif
+#ifndef FSCL_CHAIN_RAMP
+#define FSCL_CHAIN_RAMP 8192
+#endif
+constexpr int kChainRamp = FSCL_CHAIN_RAMP;   // chains shorten over the last kChainRamp tasks of a launch (about 28 tasks per resident CTA slot)
 constexpr int kChain = FSCL_CHAIN;       // neighbouring cells one CTA may take in a row, each starting from the evaluated end point of the last
 constexpr int kDirect = FSCL_DIRECT;     // sites either side of the nearest one that narrow-cut candidates are summed from directly
 

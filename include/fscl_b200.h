@@ -86,7 +86,8 @@ typedef struct {
 typedef struct {
   int64_t n_scored;         /* permutations scored                         */
   int64_t n_tasks;          /* (permutation, cell) searches launched       */
-  int64_t n_grid_evals;     /* search_maxalpha calls                       */
+  int64_t n_grid_evals;     /* fscl_grid_eval points + cell searches of permutation tests (a search is 2 + bisection-steps
+                               search_maxalpha calls, 12 at -G 100000; neighbouring cells share an end point, see below) */
   int64_t n_rounds;
   int64_t n_blocks;         /* permutation blocks applied                  */
   int32_t d7_hits;          /* blocks that overshot the array end (defined behaviour) */

@@ -203,6 +203,7 @@ struct Ctx {
   double *d_pmax = nullptr;                       // piece maxima for the candidate bounds
   bool no_prune = false;                          // evaluate every coarse candidate exactly
   int block_cap = 0;
+  size_t slot_memory = (size_t)12 << 30;          // device memory the two slot sets may take together (FSCL_B200_SLOT_GB)
   bool round_log = false; int log_R[4] = {0, 0, 0, 0}, log_na[4] = {0, 0, 0, 0};   // FSCL_B200_ROUND_LOG
   bool no_chain = false;                          // every cell evaluates both end points itself (fscl_set_endpoint_sharing)
   int *d_tile_lo = nullptr, *d_tile_hi = nullptr;
@@ -638,6 +639,7 @@ extern "C" int fscl_create(const fscl_problem_t *p, void **ctx_out) {
   c->no_chain = getenv("FSCL_B200_NO_ENDPOINT_SHARING") != nullptr;
   c->round_log = getenv("FSCL_B200_ROUND_LOG") != nullptr;
   if (const char *e = getenv("FSCL_B200_BLOCK_CAP")) c->block_cap = std::max(1, atoi(e));
+  if (const char *e = getenv("FSCL_B200_SLOT_GB")) c->slot_memory = (size_t)std::min(160, std::max(1, atoi(e))) << 30;
   c->n_pad = (c->n + kTile - 1) / kTile * kTile;
   const int n_tiles = c->n_pad / kTile;
   std::vector<int> tlo(n_tiles), thi(n_tiles);
@@ -962,7 +964,6 @@ static int ensure_small(Ctx *c, int n) {
 // permuted genomes per launch already fill the GPU, cost a quarter of the memory of 256 and waste fewer
 // evaluations on cells that finish inside the round
 constexpr int kMaxRoundPerRank = 64;
-constexpr size_t kSlotMemory = (size_t)12 << 30;      // device memory the two slot sets may take together
 
 static int engine_resources(Ctx *c) {
   if (c->prep) return FSCL_OK;
@@ -987,9 +988,13 @@ static int engine_resources(Ctx *c) {
   return FSCL_OK;
 }
 
+// Permuted genomes per rank and round that fit the memory budget of the two slot sets: 12 GB by default,
+// FSCL_B200_SLOT_GB=<n> to change it (c5, 20 M sites = 400 MB per genome: 15 per set by default; a long test on such an
+// input wants 48, so that the scan of a late round outlasts the swap phase of the next one -- one CTA per permutation,
+// 19 ms at 20 M sites).  Every rank of a sharded run must use the same value: the round size follows from it.
 static int slot_limit(const Ctx *c) {
   const size_t slot_bytes = (size_t)c->n * 20;        // tiles (key, pos, runs) + classes + scratch
-  return (int)std::max<size_t>(1, std::min<size_t>(kPinSlots, kSlotMemory / 2 / slot_bytes));
+  return (int)std::max<size_t>(1, std::min<size_t>(kPinSlots, c->slot_memory / 2 / slot_bytes));
 }
 
 // Block-list capacity per permutation on the device.  A permutation of c4 (3 M sites, -b 0.1 blocks per Mb) has about

@@ -264,3 +264,26 @@ def test_tile_bounds_dominate_exact_tile_sums(api):
                 assert ub >= exact - 1e-9 * (1.0 + abs(exact)), (int(sweep), t, j, ub, exact)
                 checked += 1
     assert checked > 300
+
+
+def test_grouped_block_swaps_equal_the_sequential_swap_loop():
+    """permute_kernel applies consecutive blocks that touch no common site as one set of swaps and a self-overlapping
+    block through a closed form (tools/proto/block_groups_proto.py states its rule): same array as snp_block_permute's
+    element-by-element loop (scan-chromosome.c:365-384) on random lists where most blocks overlap something."""
+    sys.path.insert(0, os.path.join(ROOT, "tools", "proto"))
+    import block_groups_proto as bg
+    rng = np.random.default_rng(7)
+    sizes = []
+    for trial in range(200):
+        n = int(rng.integers(50, 3000))
+        blocks = []
+        for _ in range(int(rng.integers(1, 120))):
+            L = int(rng.integers(0, max(2, n // int(rng.integers(2, 40)))))
+            i, j = int(rng.integers(0, n - L + 1)), int(rng.integers(0, n - L + 1))
+            if rng.random() < 0.05:
+                j = i
+            blocks.append((i, j, L))
+        a = rng.integers(0, 1000, n)
+        assert np.array_equal(bg.apply_sequential(a, blocks), bg.apply_grouped(a, blocks)), trial
+        sizes += bg.group_sizes(blocks)
+    assert min(sizes) == 1 and max(sizes) > 4               # both single blocks and real groups occurred
